@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the LRS-PnP hot path on B200:  python bench.py --gpus N --steps K --warmup W
+
+A *step* is one ADMM outer iteration of main_LRS_PnP.py:250-362 on synthetic data: the sparse-coding
+step (implicit 8x8 stride-1 patches → Nit soft-ISTA iterations → Phi_z), the overlap sum, the SVT
+low-rank step and the closed-form X/λ update.  Metric (BASELINE.json): ISTA patch-iterations/s =
+P*Nit / step time, whole job over all N GPUs; ms_per_step = ms per outer iteration.
+
+Workload: BASELINE.json configs[3] — synthetic 512x512x191 cube (R = 262144 unfolded rows x 191
+bands), 8x8 patches stride 1 (P = 48 233 208), 50 % per-pixel Bernoulli mask, K = 256 atoms,
+Nit = 80.  N > 1: the same cube sharded as row stripes, one rank per GPU (strong scaling).
+
+--impl reference: the CPU port of the reference path (oracle/, NumPy+BLAS on all host threads) on a
+bounded patch sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, bands, mask kind, keep)
+    "cfg4": (512, 512, 191, "bernoulli", 0.5),
+    "cfg5": (1024, 1024, 224, "stripe+bernoulli", 0.75),
+    "mini": (64, 64, 32, "bernoulli", 0.5),
+}
+K_ATOMS, NIT, BB, STRIDE = 256, 80, 8, 1
+METRIC, UNIT = "ista_patch_iters_per_s", "patch-iters/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sust=1400.0, src="fallback")
+
+
+def make_inputs(workload):
+    from lrs_pnp_dip_b200 import synth
+
+    H, W, B, kind, keep = WORKLOADS[workload]
+    clean, noisy = synth.synthetic_cube(H, W, B, rank=8, seed=0)
+    pm = synth.pixel_mask(H, W, kind, keep=keep, seed=3)
+    Y = synth.observe(noisy, pm)
+    del clean, noisy
+    D = synth.synthetic_dictionary(BB * BB, K_ATOMS, seed=0)
+    return Y, pm, D
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_patch_iters_per_s(Y, pm, D, budget_s=15.0, threads=None):
+    """Oracle port (NumPy restatement of the reference path, BLAS threads = all host cores) on a
+    bounded sample: whole rows of patches (all column starts) for a few consecutive row starts."""
+    from oracle import lrs_oracle as orc
+
+    R, C = Y.shape
+    cores = threads or os.cpu_count() or 1
+    rows = 24                                   # 17 row starts x (C-7) column starts
+    oprm = orc.Params(Nit=NIT, bb=BB, slidingDis=STRIDE, step="spectral")
+    sub = Y[:rows]
+    t_best, P_s = None, None
+    t_end = time.perf_counter() + budget_s
+    while True:
+        t0 = time.perf_counter()
+        phi, _ = orc.sparse_step(sub, np.zeros_like(sub), sub, D, oprm)
+        dt = time.perf_counter() - t0
+        P_s = phi.shape[1]
+        t_best = dt if t_best is None else min(t_best, dt)
+        if time.perf_counter() + dt > t_end:
+            break
+        if dt < budget_s / 8 and rows < 4096:   # grow the sample until one pass takes a few seconds
+            rows = min(4096, rows * 2)
+            sub = Y[:rows]
+            t_best = None
+    return P_s * NIT / t_best, cores, f"{P_s} patches ({rows} unfolded rows x all column starts) x {NIT} iterations, best pass"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    Y, pm, D = make_inputs(args.workload)
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_patch_iters_per_s(Y, pm, D, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(v)
+    val = float(np.mean(vals))
+    R, C = Y.shape
+    P = (R - BB + 1) * (C - BB + 1)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * P * NIT / val, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "note": "ms_per_step extrapolated from the sample to all P patches"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w):
+    H, W, B, kind, keep = WORKLOADS[w]
+    return f"{w}: synthetic {H}x{W}x{B} cube, 8x8 patches stride 1, {kind} mask keep={keep}, K={K_ATOMS}, Nit={NIT}"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def measure_tf32_peak(torch, seconds=1.5):
+    """Dense TF32 matmul throughput on this GPU (torch.matmul 8192^3, TF32 allowed), sustained over
+    `seconds` — the denominator of the 3xTF32 roofline."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device="cuda")
+    b = torch.randn(n, n, device="cuda")
+    for _ in range(3):
+        a @ b
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters, t0 = 0, time.perf_counter()
+    e0.record()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(10):
+            a @ b
+        iters += 10
+        torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    torch.backends.cuda.matmul.allow_tf32 = old
+    return 2.0 * n ** 3 * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import lrs_pnp_dip_b200 as lrs
+    from lrs_pnp_dip_b200 import _lib, solver
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    Y, pm, D = make_inputs(args.workload)
+    R, C = Y.shape
+    P_total = (R - BB + 1) * (C - BB + 1)
+    prm = lrs.Params(Nit=NIT, bb=BB, slidingDis=STRIDE, step="spectral")
+    st = solver.make_stripe(R, BB, rank, world)
+    Yl = np.ascontiguousarray(Y[st.row_slice])
+    Ml = np.ascontiguousarray(np.repeat(pm[st.row_slice].astype(np.float32)[:, None], C, axis=1))
+    P_local = (st.b - st.a) * (C - BB + 1)
+
+    sol = lrs.LRSPnP(torch.from_numpy(Yl), torch.from_numpy(Ml), torch.from_numpy(D), prm, engine=args.engine,
+                     stripe=st if world > 1 else None, device=dev)
+    coder = sol.be.coder
+    # time the dominant kernel (fused sparse step) with CUDA events on the launching stream
+    kern_ev = []
+    orig_phi = coder.phi_z
+
+    def timed_phi(X, l1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_phi(X, l1)
+        e1.record()
+        kern_ev.append((e0, e1))
+        return out
+
+    coder.phi_z = timed_phi
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sol.step()
+    barrier()
+    kern_ev.clear()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lrs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sol.step()
+    e1.record()
+    barrier()
+    launches = int(L.lrs_launch_count() - launches0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    kms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = P_total * NIT / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-facing call: host buffers in, host buffers out, every step ----
+    h2d = d2h = 0
+    e2e_value = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        hY, hM = pin(Yl), pin(Ml)
+        hX, hL1, hL2 = pin(Yl.copy()), pin(np.zeros_like(Yl)), pin(np.zeros_like(Yl))
+        oX = torch.empty_like(hX).pin_memory()
+        oL1, oL2 = torch.empty_like(hX).pin_memory(), torch.empty_like(hX).pin_memory()
+        Dd = torch.from_numpy(D).to(dev)
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            dY, dM = hY.to(dev, non_blocking=True), hM.to(dev, non_blocking=True)
+            s2 = lrs.LRSPnP(dY, dM, Dd, prm, engine=args.engine, stripe=st if world > 1 else None, device=dev)
+            s2.X.copy_(hX, non_blocking=True)
+            s2.lambda_1.copy_(hL1, non_blocking=True)
+            s2.lambda_2.copy_(hL2, non_blocking=True)
+            s2.step()
+            oX.copy_(s2.X, non_blocking=True)
+            oL1.copy_(s2.lambda_1, non_blocking=True)
+            oL2.copy_(s2.lambda_2, non_blocking=True)
+            h2d = 5 * hY.numel() * 4
+            d2h = 3 * hY.numel() * 4
+
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        e2e_step()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        t1.record()
+        barrier()
+        ems = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e_value = P_total * NIT / (float(ems.item()) / n_e2e * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        tf32 = measure_tf32_peak(torch)
+        flops = 4.0 * 64 * K_ATOMS * P_local * NIT + 2.0 * 64 * K_ATOMS * P_local   # ISTA + Phi_z = D alpha
+        achieved = flops / (float(kms.item()) * 1e-3) / 1e12
+        peak = tf32 / 3.0
+        cpu_v, cores, sample = (None, None, None)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu_v, cores, sample = cpu_patch_iters_per_s(Y, pm, D, budget_s=args.cpu_seconds)
+            cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor / fp32 FFMA, fp32 accumulate)" if coder.engine != 1 else "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "patches": P_total, "engine": args.engine,
+                       "step_constant": "spectral", "parallelism": f"row-stripes x{world}",
+                       "l2": "inputs exceed L2 (Phi_z alone is %.1f GB per step)" % (64 * P_local * 4 / 1e9)},
+            "clocks": clocks,
+            "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                                   "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "fused sparse step", "kernel_ms": float(kms.item()),
+                         "peak_source": f"torch TF32 matmul 8192^3 sustained on this GPU ({tf32:.0f} TFLOP/s) / 3 (3xTF32); "
+                                        f"MEASURED_PEAKS bf16 {pk['bf16_sust']:.0f} sustained ({pk['src']})"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

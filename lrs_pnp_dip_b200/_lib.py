@@ -1,0 +1,92 @@
+"""ctypes binding of csrc/liblrs_pnp.so (C ABI declared in include/lrs_pnp.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C
+lrs_pnp_dip_b200/csrc``.  There is no CPU or PyTorch fallback: if the shared
+object is missing, or a compute entry point is called without a CUDA device,
+the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblrs_pnp.so")
+
+STEP_SPECTRAL, STEP_FROB4 = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_f = C.c_float
+
+# name -> (restype, argtypes); mirrors include/lrs_pnp.h one to one
+SIGNATURES = {
+    "lrs_last_error": (C.c_char_p, []),
+    "lrs_version": (_int, []),
+    "lrs_launch_count": (C.c_uint64, []),
+    "lrs_axis_count": (_i64, [_i64, _int, _int]),
+    "lrs_axis_starts": (_int, [_i64, _int, _int, C.POINTER(_i64), _i64]),
+    "lrs_patch_index_i64": (_int, [_i64, _i64, _int, _int, _p, _p, _p, _p]),
+    "lrs_im2col_f32": (_int, [_p, _p, _f, _i64, _i64, _int, _int, _p, _p]),
+    "lrs_col2im_accum_f32": (_int, [_p, _i64, _i64, _int, _int, _p, _p]),
+    "lrs_coverage_weight_f32": (_int, [_i64, _i64, _int, _int, _p, _p]),
+    "lrs_soft_f32": (_int, [_p, _f, _p, _i64, _p]),
+    "lrs_axpy_f32": (_int, [_p, _p, _f, _p, _i64, _p]),
+    "lrs_step_frob4_f32": (_int, [_p, _p, _int, _int, _i64, _p, _p]),
+    "lrs_ista_workspace_bytes": (C.c_size_t, [_int, _int, _i64]),
+    "lrs_ista_soft_f32": (_int, [_p, _p, _p, _p, _f, _int, _int, _int, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "lrs_sparse_step_fused_f32": (_int, [_p, _p, _f, _p, _p, _int, _p, _p, _f, _int, _i64, _i64, _int, _int, _i64,
+                                         _i64, _p, _int, _p]),
+    "lrs_admm_update_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i64, _i64, _i64, _i64, _int, _int, _p]),
+    "lrs_gram_f64": (_int, [_p, _p, _f, _i64, _i64, _p, _p]),
+    "lrs_svt_apply_f32": (_int, [_p, _p, _f, _p, _i64, _i64, _p, _p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class LrsError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise LrsError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C lrs_pnp_dip_b200/csrc`. There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().lrs_last_error()
+        raise LrsError(f"{what or 'liblrs_pnp'} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise LrsError("lrs_pnp_dip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,330 @@
+// Patch geometry, im2col / col2im and the elementwise ADMM kernels (all HBM-bound).
+#include <atomic>
+
+#include "common.cuh"
+
+namespace lrs {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string& msg) { g_err = msg; }
+
+int fail_arg(const char* fn, const char* what) {
+    g_err = std::string(fn) + ": " + what;
+    return LRS_E_ARG;
+}
+
+int check_cuda(const char* fn, cudaError_t e) {
+    if (e == cudaSuccess) return LRS_OK;
+    g_err = std::string(fn) + ": CUDA error: " + cudaGetErrorString(e);
+    return LRS_E_CUDA;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_index / y_index / idx_Mat   (main_LRS_PnP.py:76-99)
+// ------------------------------------------------------------------------------------------------
+__global__ void patch_index_kernel(Geom g, int64_t* __restrict__ xi, int64_t* __restrict__ yi) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= g.P) return;
+    int64_t ci = p / g.row.n, ri = p - ci * g.row.n;
+    if (xi) xi[p] = g.row.start(ri);
+    if (yi) yi[p] = g.col.start(ci);
+}
+
+__global__ void idx_mat_kernel(Geom g, float* __restrict__ m) {
+    int64_t nr = g.R - g.bb + 1, nc = g.C - g.bb + 1;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nr * nc) return;
+    int64_t r = i / nc, c = i - r * nc;
+    bool rsel = (r % g.row.s == 0) || (g.row.n > g.row.n_reg && r == g.row.last);
+    bool csel = (c % g.col.s == 0) || (g.col.n > g.col.n_reg && c == g.col.last);
+    m[i] = (rsel && csel) ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col: blocks[(i + bb*j)*P + p] = V[(rs+i)*C + cs + j],  V = X (+ L/mu)
+// thread = (patch p, window column j); loops the bb rows.  Writes are coalesced along p.
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(Geom g, const float* __restrict__ X, const float* __restrict__ L, float mu,
+                              float* __restrict__ blocks) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (p >= g.P) return;
+    int64_t ci = p / g.row.n, ri = p - ci * g.row.n;
+    int64_t rs = g.row.start(ri), cs = g.col.start(ci);
+    const int bb = g.bb;
+    for (int i = 0; i < bb; ++i) {
+        int64_t src = (rs + i) * g.C + cs + j;
+        float v = __ldg(X + src);
+        if (L) v = __fadd_rn(v, __fdiv_rn(__ldg(L + src), mu));
+        blocks[(int64_t)(i + bb * j) * g.P + p] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// col2im: deterministic gather.  Each output element sums its covering patches in ascending patch
+// order (column start outer, row start inner) with plain fp32 adds — the order of the sequential
+// loop at main_LRS_PnP.py:332-339, so the result is bit-identical to it.
+// 32x32 tile, threads run along r while gathering (coalesced along p), transposed through shared
+// memory so the store runs along c.
+// ------------------------------------------------------------------------------------------------
+__global__ void col2im_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    int64_t r0 = blockIdx.x * 32LL, c0 = blockIdx.y * 32LL;
+    int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (32, 8)
+    for (int cc = ty; cc < 32; cc += 8) {
+        int64_t r = r0 + tx, c = c0 + cc;
+        float sum = 0.0f;
+        if (r < g.R && c < g.C) {
+            int64_t rlo, rhi, clo, chi;
+            bool rapp, capp;
+            g.row.cover(r, rlo, rhi, rapp);
+            g.col.cover(c, clo, chi, capp);
+            int64_t nci = (chi - clo + 1 > 0 ? chi - clo + 1 : 0) + (capp ? 1 : 0);
+            int64_t nri = (rhi - rlo + 1 > 0 ? rhi - rlo + 1 : 0) + (rapp ? 1 : 0);
+            for (int64_t a = 0; a < nci; ++a) {
+                int64_t ci = (capp && a == nci - 1) ? g.col.n_reg : clo + a;
+                int j = (int)(c - g.col.start(ci));
+                for (int64_t b = 0; b < nri; ++b) {
+                    int64_t ri = (rapp && b == nri - 1) ? g.row.n_reg : rlo + b;
+                    int i = (int)(r - g.row.start(ri));
+                    sum = __fadd_rn(sum, __ldg(blocks + (int64_t)(i + g.bb * j) * g.P + ci * g.row.n + ri));
+                }
+            }
+        }
+        tile[cc][tx] = sum;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        int64_t r = r0 + rr, c = c0 + tx;
+        if (r < g.R && c < g.C) out[r * g.C + c] = tile[tx][rr];
+    }
+}
+
+__global__ void weight_kernel(Geom g, float* __restrict__ w) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= g.R * g.C) return;
+    int64_t r = i / g.C, c = i - r * g.C;
+    w[i] = (float)(g.row.count(r) * g.col.count(c));
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------------
+__global__ void soft_kernel(const float* __restrict__ x, float tau, float* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = soft_thr(x[i], tau);
+}
+
+__global__ void soft_kernel_v4(const float4* __restrict__ x, float tau, float4* __restrict__ out, int64_t n4) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        float4 v = x[i];
+        v.x = soft_thr(v.x, tau);
+        v.y = soft_thr(v.y, tau);
+        v.z = soft_thr(v.z, tau);
+        v.w = soft_thr(v.w, tau);
+        out[i] = v;
+    }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, const float* __restrict__ l, float c,
+                            float* __restrict__ out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __fadd_rn(x[i], __fmul_rn(c, l[i]));
+}
+
+__global__ void step_frob4_kernel(const float* __restrict__ bc, const float* __restrict__ D, int n, int K, int64_t P,
+                                  float* __restrict__ a) {
+    extern __shared__ float rn[];  // ||D[i,:]||^2
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) {
+            float d = D[(int64_t)i * K + k];
+            s = fmaf(d, d, s);
+        }
+        rn[i] = s;
+    }
+    __syncthreads();
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float s = 0.f;
+    for (int i = 0; i < n; ++i)
+        if (bc[(int64_t)i * P + p] != 0.0f) s += rn[i];
+    a[p] = 4.0f * s;
+}
+
+// X / multiplier update, main_LRS_PnP.py:346,361-362 — same fp32 operation order, no FMA contraction.
+__global__ void admm_update_kernel(Geom g, const float* __restrict__ Y, const float* __restrict__ M,
+                                   const float* __restrict__ IM, const float* __restrict__ U, float* __restrict__ lam1,
+                                   float* __restrict__ lam2, float* __restrict__ Xo, float gamma, float mu1, float mu2,
+                                   int64_t rows, int64_t row_offset) {
+    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= rows * g.C) return;
+    int64_t r = idx / g.C, c = idx - r * g.C;
+    int W = g.row.count(r + row_offset) * g.col.count(c);
+    float l1 = lam1[idx], l2 = lam2[idx], im = IM[idx], u = U[idx];
+    float l1s = 0.0f;
+    for (int t = 0; t < W; ++t) l1s = __fadd_rn(l1s, l1);  // lambda1_summation (:343), one add per covering patch
+    float num = __fadd_rn(__fmul_rn(gamma, Y[idx]), __fmul_rn(mu1, im));
+    num = __fadd_rn(num, __fmul_rn(mu2, u));
+    num = __fsub_rn(num, l1s);
+    num = __fsub_rn(num, l2);
+    float den = __fadd_rn(__fadd_rn(__fmul_rn(gamma, M[idx]), __fmul_rn(mu1, (float)W)), mu2);
+    float x = __fdiv_rn(num, den);
+    Xo[idx] = x;
+    lam1[idx] = __fadd_rn(l1, __fmul_rn(mu1, __fsub_rn(x, im)));
+    lam2[idx] = __fadd_rn(l2, __fmul_rn(mu2, __fsub_rn(x, u)));
+}
+
+static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace lrs
+
+using namespace lrs;
+
+extern "C" {
+
+const char* lrs_last_error(void) { return lrs::g_err.c_str(); }
+
+int lrs_version(void) { return 100; }
+
+uint64_t lrs_launch_count(void) { return (uint64_t)lrs::g_launches.load(); }
+
+int64_t lrs_axis_count(int64_t length, int bb, int s) {
+    Axis a;
+    if (!make_axis(length, bb, s, a)) return -1;
+    return a.n;
+}
+
+int lrs_axis_starts(int64_t length, int bb, int s, int64_t* starts_out, int64_t count) {
+    Axis a;
+    if (!make_axis(length, bb, s, a)) return fail_arg("lrs_axis_starts", "need 0 < bb <= length and s > 0");
+    if (count != a.n || !starts_out) return fail_arg("lrs_axis_starts", "count does not match lrs_axis_count");
+    for (int64_t i = 0; i < a.n; ++i) starts_out[i] = a.start(i);
+    return LRS_OK;
+}
+
+int lrs_patch_index_i64(int64_t R, int64_t C, int bb, int s, int64_t* x_index_dev, int64_t* y_index_dev,
+                        float* idx_mat_dev, lrs_stream_t stream) {
+    Geom g;
+    if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_patch_index_i64", "need 0 < bb <= min(R,C) and s > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_index_dev || y_index_dev) {
+        patch_index_kernel<<<blocks_for(g.P, 256), 256, 0, st>>>(g, x_index_dev, y_index_dev);
+        LRS_CHECK_LAUNCH("lrs_patch_index_i64");
+    }
+    if (idx_mat_dev) {
+        int64_t tot = (R - bb + 1) * (C - bb + 1);
+        idx_mat_kernel<<<blocks_for(tot, 256), 256, 0, st>>>(g, idx_mat_dev);
+        LRS_CHECK_LAUNCH("lrs_patch_index_i64");
+    }
+    return LRS_OK;
+}
+
+int lrs_im2col_f32(const float* X_dev, const float* L_dev, float mu, int64_t R, int64_t C, int bb, int s,
+                   float* blocks_dev, lrs_stream_t stream) {
+    Geom g;
+    if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_im2col_f32", "need 0 < bb <= min(R,C) and s > 0");
+    if (!X_dev || !blocks_dev) return fail_arg("lrs_im2col_f32", "null pointer");
+    if (L_dev && mu == 0.0f) return fail_arg("lrs_im2col_f32", "mu must be non-zero");
+    dim3 grid(blocks_for(g.P, 128), bb);
+    im2col_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, X_dev, L_dev, mu, blocks_dev);
+    LRS_CHECK_LAUNCH("lrs_im2col_f32");
+    return LRS_OK;
+}
+
+int lrs_col2im_accum_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, int s, float* imout_dev,
+                         lrs_stream_t stream) {
+    Geom g;
+    if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_col2im_accum_f32", "need 0 < bb <= min(R,C) and s > 0");
+    if (!blocks_dev || !imout_dev) return fail_arg("lrs_col2im_accum_f32", "null pointer");
+    dim3 grid(blocks_for(R, 32), blocks_for(C, 32));
+    if (grid.y > 65535) return fail_arg("lrs_col2im_accum_f32", "C too large");
+    col2im_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
+    LRS_CHECK_LAUNCH("lrs_col2im_accum_f32");
+    return LRS_OK;
+}
+
+int lrs_coverage_weight_f32(int64_t R, int64_t C, int bb, int s, float* weight_dev, lrs_stream_t stream) {
+    Geom g;
+    if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_coverage_weight_f32", "need 0 < bb <= min(R,C) and s > 0");
+    if (!weight_dev) return fail_arg("lrs_coverage_weight_f32", "null pointer");
+    weight_kernel<<<blocks_for(R * C, 256), 256, 0, (cudaStream_t)stream>>>(g, weight_dev);
+    LRS_CHECK_LAUNCH("lrs_coverage_weight_f32");
+    return LRS_OK;
+}
+
+int lrs_soft_f32(const float* x_dev, float tau, float* out_dev, int64_t count, lrs_stream_t stream) {
+    if (count < 0 || (count > 0 && (!x_dev || !out_dev))) return fail_arg("lrs_soft_f32", "bad arguments");
+    if (count == 0) return LRS_OK;
+    int sms = device_sm_count();
+    if (sms <= 0) return check_cuda("lrs_soft_f32", cudaErrorNoDevice);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool v4 = ((uintptr_t)x_dev % 16 == 0) && ((uintptr_t)out_dev % 16 == 0) && (count % 4 == 0);
+    if (v4) {
+        int64_t n4 = count / 4;
+        unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sms * 16);
+        soft_kernel_v4<<<grid, 256, 0, st>>>((const float4*)x_dev, tau, (float4*)out_dev, n4);
+    } else {
+        unsigned grid = (unsigned)std::min<int64_t>((count + 255) / 256, (int64_t)sms * 16);
+        soft_kernel<<<grid, 256, 0, st>>>(x_dev, tau, out_dev, count);
+    }
+    LRS_CHECK_LAUNCH("lrs_soft_f32");
+    return LRS_OK;
+}
+
+int lrs_axpy_f32(const float* x_dev, const float* l_dev, float c, float* out_dev, int64_t count, lrs_stream_t stream) {
+    if (count < 0 || (count > 0 && (!x_dev || !l_dev || !out_dev))) return fail_arg("lrs_axpy_f32", "bad arguments");
+    if (count == 0) return LRS_OK;
+    int sms = device_sm_count();
+    if (sms <= 0) return check_cuda("lrs_axpy_f32", cudaErrorNoDevice);
+    unsigned grid = (unsigned)std::min<int64_t>((count + 255) / 256, (int64_t)sms * 16);
+    axpy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_dev, l_dev, c, out_dev, count);
+    LRS_CHECK_LAUNCH("lrs_axpy_f32");
+    return LRS_OK;
+}
+
+int lrs_step_frob4_f32(const float* blocks_copy_dev, const float* D_dev, int n, int K, int64_t P, float* a_dev,
+                       lrs_stream_t stream) {
+    if (n <= 0 || K <= 0 || P < 0 || !blocks_copy_dev || !D_dev || !a_dev)
+        return fail_arg("lrs_step_frob4_f32", "bad arguments");
+    if (P == 0) return LRS_OK;
+    if ((size_t)n * sizeof(float) > 48 * 1024) return fail_arg("lrs_step_frob4_f32", "n too large");
+    step_frob4_kernel<<<blocks_for(P, 128), 128, n * sizeof(float), (cudaStream_t)stream>>>(blocks_copy_dev, D_dev, n, K,
+                                                                                         P, a_dev);
+    LRS_CHECK_LAUNCH("lrs_step_frob4_f32");
+    return LRS_OK;
+}
+
+int lrs_admm_update_f32(const float* Y_dev, const float* MtM_dev, const float* imout_dev, const float* U_dev,
+                        float* lam1_dev, float* lam2_dev, float* X_out_dev, float gamma, float mu_1, float mu_2,
+                        int64_t rows, int64_t row_offset, int64_t R_total, int64_t C, int bb, int s,
+                        lrs_stream_t stream) {
+    Geom g;
+    if (!make_geom(R_total, C, bb, s, g)) return fail_arg("lrs_admm_update_f32", "need 0 < bb <= min(R,C) and s > 0");
+    if (rows < 0 || row_offset < 0 || row_offset + rows > R_total)
+        return fail_arg("lrs_admm_update_f32", "row stripe outside the matrix");
+    if (rows == 0) return LRS_OK;
+    if (!Y_dev || !MtM_dev || !imout_dev || !U_dev || !lam1_dev || !lam2_dev || !X_out_dev)
+        return fail_arg("lrs_admm_update_f32", "null pointer");
+    admm_update_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
+        g, Y_dev, MtM_dev, imout_dev, U_dev, lam1_dev, lam2_dev, X_out_dev, gamma, mu_1, mu_2, rows, row_offset);
+    LRS_CHECK_LAUNCH("lrs_admm_update_f32");
+    return LRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// Batched soft-ISTA on explicit patch matrices, any (n, K, P): two fp32 GEMM launches per
+// iteration with the mask / residual / step / soft-threshold fused into the epilogues.
+// This is the shape-generic engine (bundled configs: n = 1296, P = 144); the n = 64 stride-1 regime
+// goes through sparse_fused_*.cu instead.
+//
+//   residual:  Rm[n,P] = m .* (Y - D A) * inv_a[p]          (A-operand D [n,K] row-major)
+//   gradient:  A[K,P]  = soft(A + D^T Rm, T[p])             (A-operand D^T, read from D)
+//   output:    Phi[n,P] = D A                               (full dictionary, main_LRS_PnP.py:294)
+#include "common.cuh"
+
+namespace lrs {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+struct EpiResidual {  // c = D A  ->  Rm
+    const float* Y;
+    const float* BC;
+    const float* inv_a;
+    float* out;
+    __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const {
+        int64_t o = m * ld + p;
+        float v = (BC[o] != 0.0f) ? (Y[o] - acc) * inv_a[p] : 0.0f;
+        out[o] = v;
+    }
+};
+struct EpiGradient {  // c = D^T Rm  ->  A = soft(A + c, T)
+    const float* T;
+    float* A;
+    __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const {
+        int64_t o = m * ld + p;
+        A[o] = soft_thr(A[o] + acc, T[p]);
+    }
+};
+struct EpiStore {
+    float* out;
+    __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const { out[m * ld + p] = acc; }
+};
+struct LoadPlain {
+    const float* B;
+    __device__ __forceinline__ float operator()(int64_t o) const { return __ldg(B + o); }
+};
+struct LoadAxpy {  // Z = X + c*L on the fly (SVT input, main_LRS_PnP.py:315)
+    const float* X;
+    const float* L;
+    float c;
+    __device__ __forceinline__ float operator()(int64_t o) const {
+        float v = __ldg(X + o);
+        if (L) v = __fadd_rn(v, __fmul_rn(c, __ldg(L + o)));
+        return v;
+    }
+};
+
+// C[M,N] = op(A)[M,Kd] * B[Kd,N];  A stored row-major [M,Kd] (TRANS_A=false) or [Kd,M] (true).
+template <bool TRANS_A, class ALoad, class Epi>
+__global__ void __launch_bounds__(256) sgemm_kernel(ALoad aload, const float* __restrict__ B, int64_t M, int64_t N,
+                                                    int64_t Kd, Epi epi) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int64_t m0 = blockIdx.y * (int64_t)BM, n0 = blockIdx.x * (int64_t)BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int64_t k0 = 0; k0 < Kd; k0 += BK) {
+        // A tile -> As[k][m]
+        if (TRANS_A) {
+#pragma unroll
+            for (int e = tid; e < BK * BM; e += 256) {
+                int k = e / BM, m = e % BM;
+                int64_t gk = k0 + k, gm = m0 + m;
+                As[k][m] = (gk < Kd && gm < M) ? aload(gk * M + gm) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int e = tid; e < BK * BM; e += 256) {
+                int m = e / BK, k = e % BK;
+                int64_t gk = k0 + k, gm = m0 + m;
+                As[k][m] = (gk < Kd && gm < M) ? aload(gm * Kd + gk) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int e = tid; e < BK * BN; e += 256) {
+            int k = e / BN, n = e % BN;
+            int64_t gk = k0 + k, gn = n0 + n;
+            Bs[k][n] = (gk < Kd && gn < N) ? __ldg(B + gk * N + gn) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int64_t gm = m0 + ty * TM + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int64_t gn = n0 + tx * TN + j;
+            if (gn < N) epi(gm, gn, N, acc[i][j]);
+        }
+    }
+}
+
+__global__ void ista_prepare_kernel(const float* __restrict__ a, float lambda, int64_t P, float* __restrict__ inv_a,
+                                    float* __restrict__ T) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float av = a[p];
+    bool ok = av > 0.0f;
+    inv_a[p] = ok ? __fdiv_rn(1.0f, av) : 0.0f;
+    T[p] = ok ? __fdiv_rn(lambda, __fmul_rn(2.0f, av)) : 0.0f;  // T = lambda/(2a), ista.m:17
+}
+
+template <bool TRANS_A, class ALoad, class Epi>
+static int launch_gemm(const char* fn, ALoad al, const float* B, int64_t M, int64_t N, int64_t Kd, Epi epi,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
+    if (grid.y > 65535) return fail_arg(fn, "matrix too tall for this engine");
+    sgemm_kernel<TRANS_A, ALoad, Epi><<<grid, 256, 0, st>>>(al, B, M, N, Kd, epi);
+    note_launch();
+    return check_cuda(fn, cudaGetLastError());
+}
+
+// U[R,C] = (X + c L) W   — the recomposition GEMM of the Gram-based SVT (svt.cu declares it).
+int svt_apply_impl(const float* X, const float* L, float c, const float* W, int64_t R, int64_t C, float* U,
+                   cudaStream_t st) {
+    // rows of Z play "M", W is the [Kd,N] operand
+    dim3 grid((unsigned)((C + BN - 1) / BN), 1);
+    int64_t rows_per_launch = 65535LL * BM;
+    for (int64_t r0 = 0; r0 < R; r0 += rows_per_launch) {
+        int64_t rows = R - r0 < rows_per_launch ? R - r0 : rows_per_launch;
+        LoadAxpy al{X + r0 * C, L ? L + r0 * C : nullptr, c};
+        int rc = launch_gemm<false>("lrs_svt_apply_f32", al, W, rows, C, C, EpiStore{U + r0 * C}, st);
+        if (rc != LRS_OK) return rc;
+    }
+    return LRS_OK;
+}
+
+}  // namespace lrs
+
+using namespace lrs;
+
+extern "C" {
+
+size_t lrs_ista_workspace_bytes(int n, int K, int64_t P) {
+    if (n <= 0 || K <= 0 || P < 0) return 0;
+    // coefs [K,P] + residual [n,P] + inv_a [P] + T [P], each 256-byte aligned
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    return al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4);
+}
+
+int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
+                      float lambda_ista, int Nit, int n, int K, int64_t P, float* coefs_dev, float* phi_z_dev,
+                      void* workspace_dev, size_t workspace_bytes, lrs_stream_t stream) {
+    const char* fn = "lrs_ista_soft_f32";
+    if (n <= 0 || K <= 0 || P < 0 || Nit < 0) return fail_arg(fn, "bad shape");
+    if (!blocks_dev || !blocks_copy_dev || !D_dev || !a_dev) return fail_arg(fn, "null pointer");
+    if (P == 0) return LRS_OK;
+    if (workspace_bytes < lrs_ista_workspace_bytes(n, K, P) || !workspace_dev) {
+        set_error(std::string(fn) + ": workspace smaller than lrs_ista_workspace_bytes()");
+        return LRS_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    char* w = (char*)workspace_dev;
+    float* A = (float*)w;
+    w += al((size_t)K * P * 4);
+    float* Rm = (float*)w;
+    w += al((size_t)n * P * 4);
+    float* inv_a = (float*)w;
+    w += al((size_t)P * 4);
+    float* T = (float*)w;
+
+    int rc = check_cuda(fn, cudaMemsetAsync(A, 0, (size_t)K * P * 4, st));  // x0 = 0  (ista.m:14)
+    if (rc != LRS_OK) return rc;
+    ista_prepare_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a_dev, lambda_ista, P, inv_a, T);
+    LRS_CHECK_LAUNCH(fn);
+    for (int it = 0; it < Nit; ++it) {
+        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiResidual{blocks_dev, blocks_copy_dev, inv_a, Rm}, st);
+        if (rc != LRS_OK) return rc;
+        rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradient{T, A}, st);
+        if (rc != LRS_OK) return rc;
+    }
+    if (phi_z_dev) {
+        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiStore{phi_z_dev}, st);
+        if (rc != LRS_OK) return rc;
+    }
+    if (coefs_dev) {
+        rc = check_cuda(fn, cudaMemcpyAsync(coefs_dev, A, (size_t)K * P * 4, cudaMemcpyDeviceToDevice, st));
+        if (rc != LRS_OK) return rc;
+    }
+    return LRS_OK;
+}
+
+}  // extern "C"

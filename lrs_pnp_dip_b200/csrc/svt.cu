@@ -1,0 +1,125 @@
+// Low-rank proximal step helpers (SVT, main_LRS_PnP.py:118-124) for tall-skinny Z [R, C], C = bands.
+// SVT(Z, tau) = U soft(S, tau) V^T = Z * (V diag(max(1 - tau/sigma, 0)) V^T), with V, sigma^2 from the
+// eigen-decomposition of the C x C Gram matrix Z^T Z.  The Gram matrix is accumulated in fp64 (products
+// of two fp32 are exact in fp64), the small eigh is the caller's (host code), the recomposition is a
+// fused  (X + c L) * W  GEMM.
+#include "common.cuh"
+
+namespace lrs {
+
+int svt_apply_impl(const float* X, const float* L, float c, const float* W, int64_t R, int64_t C, float* U,
+                   cudaStream_t st);
+
+constexpr int GT = 64;       // output tile (bands x bands)
+constexpr int GROWS = 16;    // rows staged per step
+
+// grid.x = upper-triangular tile pairs, grid.y = row chunks.  256 threads, 4x4 fp64 accumulators each.
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ L, float c,
+                                                   int64_t R, int64_t C, int ntile, int64_t rows_per_block,
+                                                   double* __restrict__ G) {
+    __shared__ float Zi[GROWS][GT + 4];
+    __shared__ float Zj[GROWS][GT + 4];
+    // decode (ti <= tj) from the linear pair index
+    int pair = blockIdx.x, ti = 0;
+    while (pair >= ntile - ti) {
+        pair -= ntile - ti;
+        ++ti;
+    }
+    int tj = ti + pair;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int64_t ci0 = (int64_t)ti * GT, cj0 = (int64_t)tj * GT;
+    int64_t r_begin = blockIdx.y * rows_per_block;
+    int64_t r_end = r_begin + rows_per_block < R ? r_begin + rows_per_block : R;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += GROWS) {
+#pragma unroll
+        for (int e = tid; e < GROWS * GT; e += 256) {
+            int rr = e / GT, cc = e % GT;
+            int64_t r = r0 + rr;
+            float vi = 0.f, vj = 0.f;
+            if (r < r_end) {
+                if (ci0 + cc < C) {
+                    int64_t o = r * C + ci0 + cc;
+                    vi = __ldg(X + o);
+                    if (L) vi = __fadd_rn(vi, __fmul_rn(c, __ldg(L + o)));
+                }
+                if (cj0 + cc < C) {
+                    int64_t o = r * C + cj0 + cc;
+                    vj = __ldg(X + o);
+                    if (L) vj = __fadd_rn(vj, __fmul_rn(c, __ldg(L + o)));
+                }
+            }
+            Zi[rr][cc] = vi;
+            Zj[rr][cc] = vj;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < GROWS; ++rr) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = (double)Zi[rr][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = (double)Zj[rr][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t gi = ci0 + ty * 4 + i;
+        if (gi >= C) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t gj = cj0 + tx * 4 + j;
+            if (gj >= C) continue;
+            if (ti == tj) {
+                atomicAdd(G + gi * C + gj, acc[i][j]);  // diagonal tile computes both triangles itself
+            } else {
+                atomicAdd(G + gi * C + gj, acc[i][j]);
+                atomicAdd(G + gj * C + gi, acc[i][j]);
+            }
+        }
+    }
+}
+
+}  // namespace lrs
+
+using namespace lrs;
+
+extern "C" {
+
+int lrs_gram_f64(const float* X_dev, const float* L_dev, float c, int64_t R, int64_t C, double* G_dev,
+                 lrs_stream_t stream) {
+    const char* fn = "lrs_gram_f64";
+    if (R <= 0 || C <= 0 || !X_dev || !G_dev) return fail_arg(fn, "bad arguments");
+    int sms = device_sm_count();
+    if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
+    int ntile = (int)((C + GT - 1) / GT);
+    int npairs = ntile * (ntile + 1) / 2;
+    // enough row chunks to give every SM a few blocks, but at least 256 rows each
+    int64_t want_chunks = ((int64_t)sms * 4 + npairs - 1) / npairs;
+    int64_t rows_per_block = (R + want_chunks - 1) / want_chunks;
+    if (rows_per_block < 256) rows_per_block = 256;
+    rows_per_block = (rows_per_block + GROWS - 1) / GROWS * GROWS;
+    int64_t chunks = (R + rows_per_block - 1) / rows_per_block;
+    if (chunks > 65535) return fail_arg(fn, "R too large");
+    dim3 grid(npairs, (unsigned)chunks);
+    gram_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X_dev, L_dev, c, R, C, ntile, rows_per_block, G_dev);
+    LRS_CHECK_LAUNCH(fn);
+    return LRS_OK;
+}
+
+int lrs_svt_apply_f32(const float* X_dev, const float* L_dev, float c, const float* W_dev, int64_t R, int64_t C,
+                      float* U_dev, lrs_stream_t stream) {
+    if (R <= 0 || C <= 0 || !X_dev || !W_dev || !U_dev) return fail_arg("lrs_svt_apply_f32", "bad arguments");
+    return svt_apply_impl(X_dev, L_dev, c, W_dev, R, C, U_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

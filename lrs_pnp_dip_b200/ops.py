@@ -1,0 +1,260 @@
+"""The reference's own call signatures, served by the sm_100a library.
+
+Every public function here has the name, positional arguments, return arity,
+shapes, dtypes and orderings of the function it replaces in
+main_LRS_PnP.py / main_LRS_PnP_DIP_*.py / admm_utils.py (cited per function),
+so the scripts' bodies can call them unchanged.  Inputs may live on the CPU
+(as in the reference, which is CPU-only on this path) or on a CUDA device;
+outputs come back on the input's device.  All arithmetic runs in
+liblrs_pnp.so on the GPU — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+
+# ------------------------------------------------------------------ helpers
+def _to_dev(x, dtype=torch.float32) -> Tuple[torch.Tensor, torch.device, bool]:
+    """→ (contiguous CUDA tensor, original device, was_numpy)."""
+    require_cuda()
+    was_np = isinstance(x, np.ndarray)
+    t = torch.as_tensor(x)
+    src = t.device
+    if t.device.type != "cuda":
+        t = t.to("cuda", non_blocking=False)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous(), src, was_np
+
+
+def _back(t: torch.Tensor, src: torch.device, was_np: bool = False):
+    if was_np:
+        return t.cpu().numpy()
+    return t if src.type == "cuda" else t.to(src)
+
+
+def patch_grid(R: int, C: int, bb: int, s: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Selected row / column starts (host, int64) — the product set behind
+    idx_Mat, main_LRS_PnP.py:76-91."""
+    L = lib()
+    out = []
+    for length in (R, C):
+        n = L.lrs_axis_count(length, bb, s)
+        if n < 0:
+            raise _lib.LrsError(f"invalid geometry: length={length} bb={bb} stride={s}")
+        buf = (_lib.C.c_int64 * n)()
+        check(L.lrs_axis_starts(length, bb, s, buf, n), "lrs_axis_starts")
+        out.append(np.frombuffer(buf, dtype=np.int64).copy())
+    return out[0], out[1]
+
+
+def patch_count(R: int, C: int, bb: int, s: int) -> int:
+    L = lib()
+    nr, nc = L.lrs_axis_count(R, bb, s), L.lrs_axis_count(C, bb, s)
+    if nr < 0 or nc < 0:
+        raise _lib.LrsError(f"invalid geometry: R={R} C={C} bb={bb} stride={s}")
+    return int(nr * nc)
+
+
+# ------------------------------------------------------------------ get_image_block
+def im2col(X: torch.Tensor, bb: int, s: int, lambda_1: Optional[torch.Tensor] = None, mu_1: float = 1.0) -> torch.Tensor:
+    """Device-side patch matrix of ``X`` (or of ``X + lambda_1/mu_1``) ``[bb², P]``."""
+    R, C = X.shape
+    P = patch_count(R, C, bb, s)
+    out = torch.empty((bb * bb, P), dtype=torch.float32, device=X.device)
+    check(lib().lrs_im2col_f32(ptr(X), ptr(lambda_1), float(mu_1), R, C, bb, s, ptr(out), stream_ptr()), "lrs_im2col_f32")
+    return out
+
+
+def get_image_block(input_img, block_size, slidingDis):
+    """main_LRS_PnP.py:73-107 → ``(blocks [bb²,P] f32, x_index [P] int64 ndarray,
+    y_index [P] int64 ndarray, idx_Mat [R-bb+1, C-bb+1] f32)``."""
+    X, src, _ = _to_dev(input_img)
+    if X.dim() != 2:
+        raise ValueError("get_image_block expects a 2-D (pixels x bands) matrix")
+    bb, s = int(block_size), int(slidingDis)
+    R, C = X.shape
+    with torch.cuda.device(X.device):
+        P = patch_count(R, C, bb, s)
+        blocks = im2col(X, bb, s)
+        xi = torch.empty(P, dtype=torch.int64, device=X.device)
+        yi = torch.empty(P, dtype=torch.int64, device=X.device)
+        idx = torch.empty((R - bb + 1, C - bb + 1), dtype=torch.float32, device=X.device)
+        check(lib().lrs_patch_index_i64(R, C, bb, s, ptr(xi), ptr(yi), ptr(idx), stream_ptr()), "lrs_patch_index_i64")
+    return _back(blocks, src), xi.cpu().numpy(), yi.cpu().numpy(), _back(idx, src)
+
+
+def col2im(blocks: torch.Tensor, R: int, C: int, bb: int, s: int) -> torch.Tensor:
+    """Overlap sum of ``blocks [bb²,P]`` in ascending patch order
+    (main_LRS_PnP.py:332-339), bit-exact with the sequential loop."""
+    blocks = blocks.contiguous()
+    if tuple(blocks.shape) != (bb * bb, patch_count(R, C, bb, s)):
+        raise ValueError(f"blocks has shape {tuple(blocks.shape)}, geometry needs {(bb * bb, patch_count(R, C, bb, s))}")
+    out = torch.empty((R, C), dtype=torch.float32, device=blocks.device)
+    check(lib().lrs_col2im_accum_f32(ptr(blocks), R, C, bb, s, ptr(out), stream_ptr()), "lrs_col2im_accum_f32")
+    return out
+
+
+def coverage_weight(R: int, C: int, bb: int, s: int, device="cuda") -> torch.Tensor:
+    """``Weight`` of main_LRS_PnP.py:341."""
+    require_cuda()
+    out = torch.empty((R, C), dtype=torch.float32, device=device)
+    check(lib().lrs_coverage_weight_f32(R, C, bb, s, ptr(out), stream_ptr()), "lrs_coverage_weight_f32")
+    return out
+
+
+# ------------------------------------------------------------------ soft threshold family
+def _soft(x, tau):
+    t, src, was_np = _to_dev(x)
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        check(lib().lrs_soft_f32(ptr(t), float(tau), ptr(out), t.numel(), stream_ptr()), "lrs_soft_f32")
+    return _back(out, src, was_np)
+
+
+def soft_thresh(x, l):
+    """main_LRS_PnP.py:128-129."""
+    return _soft(x, l)
+
+
+def Shrinkage_Operator(X, tau):
+    """main_LRS_PnP.py:112-116."""
+    return _soft(X, tau)
+
+
+def l1_prox(input, lamda):
+    """admm_utils.py:72-75."""
+    return _soft(input, lamda)
+
+
+def delete_element(tensor, indices):
+    """main_LRS_PnP.py:152-155 — row deletion (index bookkeeping only, no arithmetic)."""
+    mask = torch.ones(tensor.size(0), dtype=torch.bool, device=tensor.device)
+    mask[torch.as_tensor(indices, dtype=torch.long, device=tensor.device)] = False
+    return tensor[mask].view((-1, tensor.size()[1]))
+
+
+# ------------------------------------------------------------------ step constants
+def spectral_norm_sq(H: torch.Tensor) -> float:
+    """``np.linalg.norm(H,2)**2`` (main_LRS_PnP.py:134) as λmax of the smaller Gram matrix, fp64 on
+    the device (one-off setup, library eigensolver)."""
+    Hd = H.to(torch.float64)
+    G = Hd @ Hd.T if Hd.shape[0] <= Hd.shape[1] else Hd.T @ Hd
+    if G.numel() == 0:
+        return 0.0
+    return float(torch.linalg.eigvalsh(G)[-1].clamp_min(0))
+
+
+def step_constants(blocks_copy: torch.Tensor, D: torch.Tensor, step: str) -> torch.Tensor:
+    """a[p] for explicit patch matrices; mask = (blocks_copy != 0), main_LRS_PnP.py:276-280.
+    'frob4': main_LRS_PnP_DIP_pro.py:190 ; 'spectral': main_LRS_PnP.py:134 (one eigensolve per
+    DISTINCT mask pattern instead of one SVD per patch per outer iteration)."""
+    n, P = blocks_copy.shape
+    K = D.shape[1]
+    a = torch.empty(P, dtype=torch.float32, device=blocks_copy.device)
+    if step == "frob4":
+        check(lib().lrs_step_frob4_f32(ptr(blocks_copy), ptr(D), n, K, P, ptr(a), stream_ptr()), "lrs_step_frob4_f32")
+        return a
+    if step != "spectral":
+        raise ValueError(f"unknown step mode {step!r}")
+    m = (blocks_copy != 0).T.contiguous()                         # [P, n] bool
+    uniq, inv = torch.unique(m, dim=0, return_inverse=True)
+    if uniq.shape[0] > 4096:
+        raise _lib.LrsError(f"{uniq.shape[0]} distinct mask patterns: spectral step constants need one eigensolve "
+                            "each; use step='frob4' or pass explicit step constants")
+    vals = torch.tensor([spectral_norm_sq(D[uniq[u]]) for u in range(uniq.shape[0])], dtype=torch.float32,
+                        device=a.device)
+    return vals[inv.reshape(-1)].contiguous()
+
+
+def row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
+    """a for each of the 2^bb validity patterns of a patch's pixel rows (band-replicated masks:
+    window element (i, j) is valid iff unfolded row r+i is observed).  bb = 8 → 256 entries."""
+    n, K = D.shape
+    assert n == bb * bb
+    i_of_k = torch.arange(n, device=D.device) % bb
+    bits = torch.arange(1 << bb, device=D.device)
+    m = ((bits[:, None] >> i_of_k[None, :]) & 1).to(torch.float64)          # [2^bb, n]
+    Dd = D.to(torch.float64)
+    if step == "frob4":
+        rn = (Dd * Dd).sum(1)
+        return (4.0 * (m @ rn)).to(torch.float32).contiguous()
+    G = Dd @ Dd.T                                                            # [n, n]
+    Gm = m[:, :, None] * G[None] * m[:, None, :]
+    return torch.linalg.eigvalsh(Gm)[:, -1].clamp_min(0).to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------ ista
+def ista_batched(blocks: torch.Tensor, blocks_copy: torch.Tensor, D: torch.Tensor, a: torch.Tensor, lambda_ista: float,
+                 Nit: int, want_coefs: bool = False, want_phi: bool = True):
+    """All patches at once (explicit patch matrices, any n / K / P).  Returns (coefs [K,P] | None,
+    phi_z [n,P] | None).  Replaces the jj loop main_LRS_PnP.py:270-303."""
+    n, P = blocks.shape
+    K = D.shape[1]
+    L = lib()
+    ws_bytes = L.lrs_ista_workspace_bytes(n, K, P)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=blocks.device)
+    coefs = torch.empty((K, P), dtype=torch.float32, device=blocks.device) if want_coefs else None
+    phi = torch.empty((n, P), dtype=torch.float32, device=blocks.device) if want_phi else None
+    check(L.lrs_ista_soft_f32(ptr(blocks), ptr(blocks_copy), ptr(D), ptr(a), float(lambda_ista), int(Nit), n, K, P,
+                              ptr(coefs), ptr(phi), ptr(ws), ws_bytes, stream_ptr()), "lrs_ista_soft_f32")
+    return coefs, phi
+
+
+def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "spectral"):
+    """main_LRS_PnP.py:131-149 / main_LRS_PnP_DIP_pro.py:188-201 / ista.m:1-24.
+    ``alpha`` is ignored and recomputed exactly as the reference does (``step='spectral'``:
+    ‖H‖₂² ; ``'frob4'``: 4‖H‖_F²).  ``denoiser='soft'`` is the MATLAB twin's soft(g, T)
+    (ista.m:23) — the NLM plug-in of the Python scripts is not provided."""
+    if denoiser != "soft":
+        raise NotImplementedError("only the soft-threshold denoiser (ista.m:23) is implemented on the device")
+    Hd, src, _ = _to_dev(H)
+    yd, _, _ = _to_dev(y)
+    yd = yd.reshape(-1, 1)
+    with torch.cuda.device(Hd.device):
+        ones = torch.ones_like(yd)
+        if step == "spectral":
+            a = torch.tensor([spectral_norm_sq(Hd)], dtype=torch.float32, device=Hd.device)
+        else:
+            a = step_constants(ones, Hd, step)
+        coefs, _ = ista_batched(yd, ones, Hd, a, lambda_ista, Nit, want_coefs=True, want_phi=False)
+    return _back(coefs, src)
+
+
+# ------------------------------------------------------------------ SVT
+def svt_weights(G: torch.Tensor, tau: float) -> torch.Tensor:
+    """W = V diag(max(1 - tau/sigma, 0)) Vᵀ from the fp64 Gram matrix (σ² = eig)."""
+    evals, V = torch.linalg.eigh(G)
+    sigma = evals.clamp_min(0).sqrt()
+    w = torch.where(sigma > tau, 1.0 - tau / sigma.clamp_min(1e-300), torch.zeros_like(sigma))
+    return ((V * w[None, :]) @ V.T).to(torch.float32).contiguous()
+
+
+def svt_device(X: torch.Tensor, tau: float, lambda_2: Optional[torch.Tensor] = None, c: float = 0.0,
+               gram_reduce=None) -> torch.Tensor:
+    """SVT(X + c*lambda_2, tau) for tall-skinny matrices: fp64 Gram (lrs_gram_f64) → eigh of the
+    C×C matrix → fused recomposition (lrs_svt_apply_f32).  ``gram_reduce`` (optional) is applied
+    to the Gram matrix before the eigh — the all-reduce hook of the sharded driver."""
+    R, Cc = X.shape
+    G = torch.zeros((Cc, Cc), dtype=torch.float64, device=X.device)
+    check(lib().lrs_gram_f64(ptr(X), ptr(lambda_2), float(c), R, Cc, ptr(G), stream_ptr()), "lrs_gram_f64")
+    if gram_reduce is not None:
+        G = gram_reduce(G)
+    W = svt_weights(G, float(tau))
+    U = torch.empty_like(X)
+    check(lib().lrs_svt_apply_f32(ptr(X), ptr(lambda_2), float(c), ptr(W), R, Cc, ptr(U), stream_ptr()), "lrs_svt_apply_f32")
+    return U
+
+
+def SVT(X, tau):
+    """main_LRS_PnP.py:118-124."""
+    Xd, src, _ = _to_dev(X)
+    with torch.cuda.device(Xd.device):
+        U = svt_device(Xd, float(tau))
+    return _back(U, src)

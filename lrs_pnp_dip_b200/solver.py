@@ -1,0 +1,326 @@
+"""Batched fast path of the ADMM outer iteration (the script body
+main_LRS_PnP.py:244-362, identical in main_LRS_PnP_DIP_pro.py:355-456 and
+main_LRS_PnP_DIP_1-LiP.py:347-448) on one B200, or on a row-stripe shard of
+the unfolded matrix per rank (one process per GPU).
+
+    coder  = SparseCoder(Y_observed, D, prm)           # once: masks, step constants
+    solver = LRSPnP(Y_observed, MtM, D, prm)           # X = Y_observed, λ1 = λ2 = 0   (:218-229)
+    solver.step()                                      # one outer iteration           (:250-362)
+
+The low-rank step is SVT (main_LRS_PnP.py:315) by default; the DIP variants pass
+``low_rank=callable(Z) -> U`` and keep their PyTorch network (out of scope here).
+
+Sharding: contiguous stripes of patch row-starts, each rank holding its
+rows plus the ``bb-1`` rows of read halo that follow.  Per outer iteration: one
+neighbour halo *reduce* of the partial overlap sums, one all-reduce of the C×C band
+Gram matrix for the SVT, one neighbour halo *refresh* of X and λ1.  Stripes are
+supported for ``slidingDis == 1`` (the multi-GPU configurations BASELINE.json
+names); other strides run unsharded.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check, lib, ptr, stream_ptr
+
+FUSED_K = (64, 128, 192, 256)
+
+
+@dataclass
+class Params:
+    """Hyper-parameters, SURVEY Appendix C.  Defaults = main_LRS_PnP.py:218-238;
+    DIP variants: mu_1 = mu_2 = 0.1, Nit = 100, step = 'frob4' (main_LRS_PnP_DIP_pro.py:324-341,190)."""
+    gamma: float = 0.5
+    mu_1: float = 0.15
+    mu_2: float = 0.15 * 6
+    lambda_ista: float = 0.1
+    Nit: int = 80
+    bb: int = 36
+    slidingDis: int = 36
+    step: str = "spectral"
+
+
+# --------------------------------------------------------------------------------------------------
+# stripe partition (host logic, no device)
+# --------------------------------------------------------------------------------------------------
+def stripe_bounds(R: int, bb: int, world: int) -> np.ndarray:
+    """Balanced split of the R-bb+1 patch row-starts (stride 1) into ``world`` contiguous stripes;
+    returns world+1 boundaries a_0=0 < ... < a_world = R-bb+1."""
+    n = R - bb + 1
+    if n < world:
+        raise ValueError(f"cannot split {n} patch rows over {world} ranks")
+    return np.array([(n * g) // world for g in range(world + 1)], dtype=np.int64)
+
+
+@dataclass
+class Stripe:
+    rank: int
+    world: int
+    R_total: int
+    bb: int
+    a: int          # first owned patch row-start (= first owned matrix row)
+    b: int          # one past the last owned patch row-start
+
+    @property
+    def halo(self) -> int:            # rows read beyond the owned patch starts
+        return self.bb - 1
+
+    @property
+    def rows_local(self) -> int:      # rows held: [a, b + bb - 1)
+        return self.b - self.a + self.bb - 1
+
+    @property
+    def rows_owned(self) -> int:      # rows whose X/λ this rank updates
+        return (self.R_total - self.a) if self.rank == self.world - 1 else (self.b - self.a)
+
+    @property
+    def row_slice(self) -> slice:
+        return slice(self.a, self.a + self.rows_local)
+
+
+def make_stripe(R: int, bb: int, rank: int, world: int) -> Stripe:
+    bd = stripe_bounds(R, bb, world)
+    return Stripe(rank=rank, world=world, R_total=R, bb=bb, a=int(bd[rank]), b=int(bd[rank + 1]))
+
+
+# --------------------------------------------------------------------------------------------------
+# sparse-coding step
+# --------------------------------------------------------------------------------------------------
+class SparseCoder:
+    """Everything of the sparse step that depends only on (Y_observed, D, geometry): the per-patch
+    validity masks (``blocks_copy == 0``, main_LRS_PnP.py:244,276-280) and the ISTA step constants,
+    which the reference recomputes for every patch in every outer iteration (:134)."""
+
+    def __init__(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str = "auto"):
+        _lib.require_cuda()
+        if Y_observed.device.type != "cuda" or D.device.type != "cuda":
+            raise _lib.LrsError("SparseCoder needs CUDA tensors")
+        self.Y = Y_observed.contiguous().float()
+        self.D = D.contiguous().float()
+        self.prm = prm
+        self.R, self.C = self.Y.shape
+        self.n, self.K = self.D.shape
+        if self.n != prm.bb * prm.bb:
+            raise ValueError(f"dictionary has {self.n} rows, bb² = {prm.bb * prm.bb}")
+        self.P = ops.patch_count(self.R, self.C, prm.bb, prm.slidingDis)
+        self.engine = _lib.ENGINES[engine]
+        self.fused = prm.bb == 8 and self.K in FUSED_K
+        self.a_patch = self.a_table = self.blocks_copy = None
+        if self.fused:
+            if prm.step == "spectral":
+                obs = self.Y != 0
+                if not bool((obs == obs[:, :1]).all()):
+                    raise _lib.LrsError("spectral step constants on the fused path need band-replicated masks "
+                                        "(one validity flag per unfolded row); use step='frob4'")
+                self.a_table = ops.row_pattern_table(self.D, prm.bb, "spectral")
+            elif prm.step != "frob4":
+                raise ValueError(prm.step)
+        else:
+            self.blocks_copy = ops.im2col(self.Y, prm.bb, prm.slidingDis)
+            self.a_patch = ops.step_constants(self.blocks_copy, self.D, prm.step)
+
+    def phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
+        """Phi_z [n, P] of main_LRS_PnP.py:259-303 for V = X + lambda_1/mu_1."""
+        prm = self.prm
+        if self.fused:
+            phi = torch.empty((self.n, self.P), dtype=torch.float32, device=X.device)
+            check(lib().lrs_sparse_step_fused_f32(ptr(X), ptr(lambda_1), float(prm.mu_1), ptr(self.Y), ptr(self.D), self.K,
+                                                  ptr(self.a_patch), ptr(self.a_table), float(prm.lambda_ista), int(prm.Nit),
+                                                  self.R, self.C, prm.bb, prm.slidingDis, 0, self.P, ptr(phi),
+                                                  self.engine, stream_ptr()), "lrs_sparse_step_fused_f32")
+            return phi
+        blocks = ops.im2col(X, prm.bb, prm.slidingDis, lambda_1, prm.mu_1)
+        _, phi = ops.ista_batched(blocks, self.blocks_copy, self.D, self.a_patch, prm.lambda_ista, prm.Nit)
+        return phi
+
+    def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
+        """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339)."""
+        return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, self.prm.bb, self.prm.slidingDis)
+
+
+def sparse_step(X, lambda_1, mu_1, Y_observed, D, bb, slidingDis, lambda_ista, Nit, step="spectral", engine="auto",
+                return_phi=False):
+    """Functional form: (IMout, Weight[, Phi_z]) for one call (builds a SparseCoder each time)."""
+    prm = Params(mu_1=mu_1, lambda_ista=lambda_ista, Nit=Nit, bb=bb, slidingDis=slidingDis, step=step)
+    sc = SparseCoder(Y_observed, D, prm, engine)
+    phi = sc.phi_z(X, lambda_1)
+    im = ops.col2im(phi, sc.R, sc.C, bb, slidingDis)
+    W = ops.coverage_weight(sc.R, sc.C, bb, slidingDis, device=X.device)
+    return (im, W, phi) if return_phi else (im, W)
+
+
+def admm_update(Y_observed, MtM, IMout, U, lambda_1, lambda_2, prm: Params, rows=None, row_offset=0, R_total=None):
+    """X / λ update (main_LRS_PnP.py:346,361-362).  λ1, λ2 are updated in place; returns X."""
+    R, C = Y_observed.shape
+    rows = R if rows is None else rows
+    R_total = R if R_total is None else R_total
+    X = torch.empty((rows, C), dtype=torch.float32, device=Y_observed.device)
+    check(lib().lrs_admm_update_f32(ptr(Y_observed), ptr(MtM), ptr(IMout), ptr(U), ptr(lambda_1), ptr(lambda_2), ptr(X),
+                                    float(prm.gamma), float(prm.mu_1), float(prm.mu_2), rows, row_offset, R_total, C,
+                                    prm.bb, prm.slidingDis, stream_ptr()), "lrs_admm_update_f32")
+    return X
+
+
+# --------------------------------------------------------------------------------------------------
+# communication shim: the three exchanges of a sharded outer iteration
+# --------------------------------------------------------------------------------------------------
+class StripeComm:
+    """Neighbour halo exchange + Gram all-reduce over torch.distributed (NCCL on GPUs, gloo in the
+    CPU tests).  world == 1 → every method is a no-op."""
+
+    def __init__(self, stripe: Stripe, group=None):
+        self.st = stripe
+        self.group = group
+
+    def _exchange(self, send_to_right: Optional[torch.Tensor], send_to_left: Optional[torch.Tensor],
+                  like: torch.Tensor) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Send tensors to the right / left neighbour; returns (from_left, from_right)."""
+        import torch.distributed as dist
+
+        st = self.st
+        ops_, from_left, from_right = [], None, None
+        if send_to_right is not None and st.rank + 1 < st.world:
+            ops_.append(dist.P2POp(dist.isend, send_to_right.contiguous(), st.rank + 1, self.group))
+        if send_to_right is not None and st.rank > 0:
+            from_left = torch.empty_like(like)
+            ops_.append(dist.P2POp(dist.irecv, from_left, st.rank - 1, self.group))
+        if send_to_left is not None and st.rank > 0:
+            ops_.append(dist.P2POp(dist.isend, send_to_left.contiguous(), st.rank - 1, self.group))
+        if send_to_left is not None and st.rank + 1 < st.world:
+            from_right = torch.empty_like(like)
+            ops_.append(dist.P2POp(dist.irecv, from_right, st.rank + 1, self.group))
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        return from_left, from_right
+
+    def halo_reduce(self, imout_local: torch.Tensor) -> None:
+        """Partial overlap sums of the halo rows go to the right neighbour, which owns them."""
+        st = self.st
+        if st.world == 1 or st.halo == 0:
+            return
+        h = st.halo
+        send = imout_local[st.rows_local - h:] if st.rank + 1 < st.world else None
+        if st.rank + 1 < st.world or st.rank > 0:
+            from_left, _ = self._exchange(send if send is not None else imout_local[:0], None, imout_local[:h])
+            if from_left is not None:
+                imout_local[:h] += from_left
+
+    def halo_refresh(self, *arrays: torch.Tensor) -> None:
+        """Owned first rows travel to the LEFT neighbour's halo (X and λ1 after the update)."""
+        st = self.st
+        if st.world == 1 or st.halo == 0:
+            return
+        h = st.halo
+        for arr in arrays:
+            send = arr[:h] if st.rank > 0 else arr[:0]
+            _, from_right = self._exchange(None, send, arr[:h])
+            if from_right is not None:
+                arr[st.rows_local - h:] = from_right
+
+    def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.st.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+# --------------------------------------------------------------------------------------------------
+# compute backend of one stripe (CUDA).  The CPU tests of the sharded driver substitute their own
+# object with the same five methods; the product never does.
+# --------------------------------------------------------------------------------------------------
+class CudaBackend:
+    def __init__(self, Y_local: torch.Tensor, MtM_local: torch.Tensor, D: torch.Tensor, prm: Params, engine="auto"):
+        self.prm = prm
+        self.Y, self.MtM = Y_local, MtM_local
+        self.coder = SparseCoder(Y_local, D, prm, engine)
+
+    def imout(self, X, lambda_1):
+        return self.coder.imout(X, lambda_1)
+
+    def gram(self, X, lambda_2, c, rows):
+        C = X.shape[1]
+        G = torch.zeros((C, C), dtype=torch.float64, device=X.device)
+        check(lib().lrs_gram_f64(ptr(X), ptr(lambda_2), float(c), rows, C, ptr(G), stream_ptr()), "lrs_gram_f64")
+        return G
+
+    def svt_apply(self, X, lambda_2, c, G, tau, rows):
+        W = ops.svt_weights(G, tau)
+        U = torch.empty((rows, X.shape[1]), dtype=torch.float32, device=X.device)
+        check(lib().lrs_svt_apply_f32(ptr(X), ptr(lambda_2), float(c), ptr(W), rows, X.shape[1], ptr(U), stream_ptr()),
+              "lrs_svt_apply_f32")
+        return U
+
+    def axpy(self, X, L, c, rows):
+        out = torch.empty((rows, X.shape[1]), dtype=torch.float32, device=X.device)
+        check(lib().lrs_axpy_f32(ptr(X), ptr(L), float(c), ptr(out), out.numel(), stream_ptr()), "lrs_axpy_f32")
+        return out
+
+    def admm_update(self, IMout, U, lambda_1, lambda_2, rows, row_offset, R_total):
+        return admm_update(self.Y, self.MtM, IMout, U, lambda_1, lambda_2, self.prm, rows, row_offset, R_total)
+
+
+class LRSPnP:
+    """ADMM driver.  ``Y_observed`` / ``MtM`` are this rank's LOCAL rows (the whole matrix when
+    unsharded).  ``low_rank``: None → SVT with τ = 1/μ2 (main_LRS_PnP.py:315); or a callable
+    ``U = low_rank(Z)`` on this rank's owned rows (the DIP variants' network, kept in PyTorch)."""
+
+    def __init__(self, Y_observed, MtM, D, prm: Params, low_rank: Optional[Callable] = None, engine: str = "auto",
+                 stripe: Optional[Stripe] = None, group=None, backend=None, device=None):
+        if backend is None:
+            _lib.require_cuda()
+            device = torch.device(device if device is not None else "cuda")
+            Y_observed = torch.as_tensor(Y_observed, dtype=torch.float32).to(device).contiguous()
+            MtM = torch.as_tensor(MtM, dtype=torch.float32).to(device).contiguous()
+            D = torch.as_tensor(D, dtype=torch.float32).to(device).contiguous()
+            backend = CudaBackend(Y_observed, MtM, D, prm, engine)
+        self.be = backend
+        self.prm = prm
+        self.Y = Y_observed
+        R_loc = Y_observed.shape[0]
+        self.stripe = stripe if stripe is not None else Stripe(0, 1, R_loc, prm.bb, 0, R_loc - prm.bb + 1)
+        if self.stripe.world > 1 and prm.slidingDis != 1:
+            raise _lib.LrsError("row-stripe sharding is implemented for slidingDis == 1")
+        if self.stripe.world > 1 and R_loc != self.stripe.rows_local:
+            raise ValueError("Y_observed must hold exactly this rank's stripe rows (owned + halo)")
+        self.comm = StripeComm(self.stripe, group)
+        self.low_rank = low_rank
+        self.X = Y_observed.clone()                      # X = Y_observed          (:229)
+        self.lambda_1 = torch.zeros_like(Y_observed)     # (:219)
+        self.lambda_2 = torch.zeros_like(Y_observed)     # (:220)
+        self.iterations = 0
+
+    @property
+    def rows_owned(self) -> int:
+        return self.stripe.rows_owned if self.stripe.world > 1 else self.Y.shape[0]
+
+    def step(self) -> None:
+        prm, st, be = self.prm, self.stripe, self.be
+        own = self.rows_owned
+        row_off = st.a if st.world > 1 else 0
+        # sparse step + overlap sum on the local rows (:259-303, :332-339)
+        IMout = be.imout(self.X, self.lambda_1)
+        self.comm.halo_reduce(IMout)
+        # low-rank step on Z = X + (1/mu_2) lambda_2 (:315)
+        c = 1.0 / prm.mu_2
+        if self.low_rank is None:
+            G = self.comm.allreduce_sum(be.gram(self.X, self.lambda_2, c, own))
+            U = be.svt_apply(self.X, self.lambda_2, c, G, 1.0 / prm.mu_2, own)
+        else:
+            U = self.low_rank(be.axpy(self.X, self.lambda_2, c, own))
+        # closed-form X, multipliers (:346, :361-362) on the owned rows
+        Xn = be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total)
+        self.X[:own] = Xn
+        self.comm.halo_refresh(self.X, self.lambda_1)
+        self.iterations += 1
+
+    def run(self, iteration_num: int) -> "LRSPnP":
+        for _ in range(iteration_num):
+            self.step()
+        return self

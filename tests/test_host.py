@@ -1,0 +1,95 @@
+"""CPU-only checks of the boundary and the host logic: the shared object loads and exports every
+symbol include/lrs_pnp.h declares, the host-side geometry entry points agree with the oracle, the
+stripe partition is consistent, and compute entry points refuse to run without a GPU (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import lrs_pnp_dip_b200 as lrs
+from lrs_pnp_dip_b200 import _lib
+from oracle import lrs_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+
+        ge.build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lrs_pnp.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lrs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.lrs_version() >= 100
+
+
+@pytest.mark.parametrize("geom", [(1296, 128, 36, 36), (64, 41, 8, 3), (64, 40, 8, 8), (50, 23, 8, 1), (37, 19, 4, 3),
+                                  (262144, 191, 8, 1), (20, 20, 3, 7), (8, 8, 8, 1)])
+def test_host_geometry_matches_oracle(geom):
+    R, C, bb, s = geom
+    rs, cs = lrs.patch_grid(R, C, bb, s)
+    assert np.array_equal(rs, orc.axis_starts(R, bb, s))
+    assert np.array_equal(cs, orc.axis_starts(C, bb, s))
+    assert lrs.patch_count(R, C, bb, s) == len(rs) * len(cs)
+
+
+def test_baseline_patch_counts():
+    assert lrs.patch_count(1296, 128, 36, 36) == 144
+    assert lrs.patch_count(262144, 191, 8, 1) == 48_233_208          # SURVEY §8 cfg 4
+    assert lrs.patch_count(1048576, 224, 8, 1) == 227_539_473        # cfg 5
+
+
+def test_bad_geometry_is_an_error():
+    with pytest.raises(lrs.LrsError):
+        lrs.patch_count(4, 100, 8, 1)
+    L = _lib.lib()
+    assert L.lrs_axis_count(10, 0, 1) < 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    x = torch.randn(40, 23)
+    with pytest.raises(lrs.LrsError):
+        lrs.get_image_block(x, 8, 1)
+    with pytest.raises(lrs.LrsError):
+        lrs.soft_thresh(np.ones(4, np.float32), 0.1)
+    with pytest.raises(lrs.LrsError):
+        lrs.LRSPnP(np.zeros((40, 23), np.float32), np.ones((40, 23), np.float32), np.zeros((64, 64), np.float32),
+                   lrs.Params(bb=8, slidingDis=1))
+    # the raw ABI reports a CUDA error rather than computing on the host
+    L = _lib.lib()
+    rc = L.lrs_soft_f32(1, 0.1, 1, 4, None)
+    assert rc == -2 and b"CUDA" in L.lrs_last_error()
+
+
+def test_delete_element_is_reference_row_deletion():
+    t = torch.arange(20.0).view(5, 4)
+    out = lrs.delete_element(t, [1, 3])
+    assert torch.equal(out, t[[0, 2, 4]])
+
+
+def test_stripe_partition():
+    for R, bb, world in [(262144, 8, 8), (1048576, 8, 8), (100, 8, 3), (64, 8, 2)]:
+        bd = lrs.stripe_bounds(R, bb, world)
+        assert bd[0] == 0 and bd[-1] == R - bb + 1 and np.all(np.diff(bd) > 0)
+        assert np.diff(bd).max() - np.diff(bd).min() <= 1
+        owned = 0
+        for g in range(world):
+            st = lrs.make_stripe(R, bb, g, world)
+            assert st.rows_local == st.b - st.a + bb - 1
+            owned += st.rows_owned
+            # local stride-1 geometry has exactly the owned patch row-starts
+            assert st.rows_local - bb + 1 == st.b - st.a
+        assert owned == R
