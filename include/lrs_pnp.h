@@ -137,6 +137,14 @@ int lrs_gram_f64(const float* X_dev, const float* L_dev, float c, int64_t R, int
 int lrs_svt_apply_f32(const float* X_dev, const float* L_dev, float c, const float* W_dev, int64_t R, int64_t C,
                       float* U_dev, lrs_stream_t stream);
 
+/* ---- diagnostics of the tcgen05 engine (no reference counterpart) ------------------------------- */
+/* C[128,N] = A[128,Kd] * B[N,Kd]^T through one CTA's tensor core with the operand layouts of the fused
+ * kernel: A from shared memory (a_in_tmem = 0) or TMEM (1); B K-major (b_mn_major = 0) or MN-major (1). */
+int lrs_tc_probe_f32(const float* A_dev, const float* B_dev, float* C_dev, int N, int Kd, int a_in_tmem,
+                     int b_mn_major, lrs_stream_t stream);
+/* Cycle counts of MMA issue chains / TMEM load-store streams; out_dev = int64 [blocks*16]. */
+int lrs_tc_microbench(int mode, int reps, int blocks, long long* out_dev, lrs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
