@@ -139,11 +139,13 @@ int lrs_svt_apply_f32(const float* X_dev, const float* L_dev, float c, const flo
 
 /* ---- diagnostics of the tcgen05 engine (no reference counterpart) ------------------------------- */
 /* C[128,N] = A[128,Kd] * B[N,Kd]^T through one CTA's tensor core with the operand layouts of the fused
- * kernel: A from shared memory (a_in_tmem = 0) or TMEM (1); B K-major (b_mn_major = 0) or MN-major (1). */
+ * kernel: A from shared memory (a_in_tmem = 0) or TMEM (1); B K-major (b_mn_major = 0) or MN-major (1),
+ * SWIZZLE_NONE; f16 = 0: kind::tf32 on the fp32 data, 1: kind::f16 on the data rounded to fp16. */
 int lrs_tc_probe_f32(const float* A_dev, const float* B_dev, float* C_dev, int N, int Kd, int a_in_tmem,
-                     int b_mn_major, lrs_stream_t stream);
+                     int b_mn_major, int f16, lrs_stream_t stream);
 /* Cycle counts of MMA issue chains / TMEM load-store streams; out_dev = int64 [blocks*16]. */
-int lrs_tc_microbench(int mode, int reps, int blocks, long long* out_dev, lrs_stream_t stream);
+int lrs_tc_microbench(int do_mma, int f16, int ts, int N, int nacc, int ldst, int depth, int reps, int blocks,
+                      long long* out_dev, lrs_stream_t stream);
 
 #ifdef __cplusplus
 }
