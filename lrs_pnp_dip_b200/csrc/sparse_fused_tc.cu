@@ -5,7 +5,7 @@
 // ista.m:13-24).  Here the two contractions of every iteration run on the 5th-generation tensor cores:
 //
 //   tile        128 consecutive patches (reference order) = the 128 TMEM lanes = MMA M
-//   GEMM-B      G[128 x 256]  = alpha + r D        accumulated IN PLACE onto the fp32 alpha in TMEM
+//   GEMM-B      G[128 x 256]  = alpha + r D        accumulated IN PLACE onto the fp32 state in TMEM
 //   epilogue    alpha = soft(G, T)                 tcgen05.ld -> registers -> tcgen05.st
 //   GEMM-A      Da[128 x 64]  = alpha D^T          A operand = alpha pieces staged in TMEM (TS form)
 //   epilogue    r = m .* (y - Da) / a              written back to TMEM as the next A operand
@@ -46,9 +46,13 @@ constexpr uint32_t COL_ALPHA = 0;    // [0,256)   fp32 alpha / GEMM-B accumulato
 constexpr uint32_t COL_ACC = 256;    // [256,320) alpha1 D1 + alpha2 D1 ; [320,384) alpha1 D2
 constexpr uint32_t COL_STG0 = 384;   // staging buffers: piece 1 in [+0,+32), piece 2 in [+32,+64)
 constexpr uint32_t COL_STG1 = 448;   //   buffer 0 also carries the residual pieces between GEMM-A and GEMM-B
-constexpr float S_ALPHA = 8.0f;      // alpha pieces = fp16(8 alpha')
-constexpr float S_D = 4.0f;          // D pieces     = fp16(4 D)
-constexpr float S_R = 0.25f;         // residual pieces = fp16(r / 4)  (S_R * S_D = 1: GEMM-B lands in alpha's units)
+// The state kept in TMEM is at = a * alpha' (alpha' = alpha / 2^ex, the patch-normalised coefficients), so that the
+// residual operand r = m .* (y' - D alpha') is O(1) whatever the step constant a is:
+//     at <- soft(at + r D, lambda' / 2),      D alpha' = (D at) / a
+// (soft is positively homogeneous: a * soft(g, T) = soft(a g, a T), and a T = lambda / 2).
+constexpr float S_ALPHA = 4.0f;      // state pieces    = fp16(4 at)
+constexpr float S_D = 4.0f;          // D pieces        = fp16(4 D)
+constexpr float S_R = 0.25f;         // residual pieces = fp16(r / 4)  (S_R * S_D = 1: GEMM-B lands in the state's units)
 
 // D pieces in shared memory, one copy for both GEMMs (bytes):
 //   (k%8)*2 + (i%8)*16 + (8*piece + i/8)*128 + (k/8)*2048       i = pixel (row of D), k = atom
@@ -219,9 +223,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             int ex = 0;
             if (amax > 0.0f) (void)frexpf(amax, &ex);          // amax = f * 2^ex, f in [0.5, 1)
             const float dn = ldexpf(1.0f, -ex), up = ldexpf(1.0f, ex);
-            const float Tn = ok_a ? __fdiv_rn(prm.lambda, __fmul_rn(2.0f, a)) * dn : 0.0f;
-            const float c1 = inv_a * S_R * dn;                    // y  -> scaled residual units
-            const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= 32 D alpha') -> scaled residual units
+            const float Tn = ok_a ? 0.5f * prm.lambda * dn : 0.0f;  // a * T = lambda / 2 (ista.m:17), normalised
+            const float c1 = S_R * dn;                            // y -> scaled residual units
+            const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= S_ALPHA S_D a D alpha') -> scaled residual units
 #pragma unroll
             for (int c = 0; c < 32; ++c) ysc[c] *= c1;
 
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 tmem_ld32(lane_addr + COL_ACC + 64 + 32 * h, a1);
                 tmem_wait_ld();
                 tc_fence_before();   // order these loads before the next tile's MMAs (via bar_R)
-                const float sc = up / (S_ALPHA * S_D);
+                const float sc = up * inv_a / (S_ALPHA * S_D);
                 if (valid) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c)
