@@ -302,7 +302,11 @@ def run_ours(args, rank, world, local_rank):
         tf32 = measure_tf32_peak(torch)
         flops = 4.0 * 64 * K_ATOMS * P_local * NIT + 2.0 * 64 * K_ATOMS * P_local   # ISTA + Phi_z = D alpha
         achieved = flops / (float(kms.item()) * 1e-3) / 1e12
-        peak = tf32 / 3.0
+        # The tcgen05 engine emulates fp32 with 3 fp16-piece MMAs per product, so its ceiling is the dense
+        # 16-bit tensor rate / 3 (driver-measured cuBLAS bf16, sustained: the kernel runs for seconds under
+        # the power cap).  The 3xTF32 ceiling the spec names (measured TF32 / 3) is reported beside it.
+        simt = (args.engine == "simt")
+        peak = pk["bf16_sust"] / 3.0
         cpu_v, cores, sample = (None, None, None)
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -311,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (3xTF32 tensor / fp32 FFMA, fp32 accumulate)" if coder.engine != 1 else "f32",
+            "dtype": "f32 (fp32 FFMA)" if simt else "f32 via 3-pass fp16 split on tcgen05 (22-bit operands, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "patches": P_total, "engine": args.engine,
                        "step_constant": "spectral", "parallelism": f"row-stripes x{world}",
@@ -322,8 +326,10 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "fused sparse step", "kernel_ms": float(kms.item()),
-                         "peak_source": f"torch TF32 matmul 8192^3 sustained on this GPU ({tf32:.0f} TFLOP/s) / 3 (3xTF32); "
-                                        f"MEASURED_PEAKS bf16 {pk['bf16_sust']:.0f} sustained ({pk['src']})"},
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained {pk['bf16_sust']:.0f} ({pk['src']}) / 3 "
+                                        "(3 fp16 MMAs per fp32 product; split products not counted as useful flops)",
+                         "tf32x3_peak": tf32 / 3.0, "frac_of_tf32x3": achieved / (tf32 / 3.0),
+                         "tf32_measured": tf32},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
