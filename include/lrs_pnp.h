@@ -143,6 +143,9 @@ int lrs_svt_apply_f32(const float* X_dev, const float* L_dev, float c, const flo
  * SWIZZLE_NONE; f16 = 0: kind::tf32 on the fp32 data, 1: kind::f16 on the data rounded to fp16. */
 int lrs_tc_probe_f32(const float* A_dev, const float* B_dev, float* C_dev, int N, int Kd, int a_in_tmem,
                      int b_mn_major, int f16, lrs_stream_t stream);
+/* Barrier-wait cycle counters of the fused tcgen05 kernel (block 0), filled when the environment variable
+ * LRS_TC_TIMING is set at the first launch; out32_host = uint64 [32] in HOST memory. */
+int lrs_tc_timing_read(unsigned long long* out32_host);
 /* Cycle counts of MMA issue chains / TMEM load-store streams; out_dev = int64 [blocks*16]. */
 int lrs_tc_microbench(int do_mma, int f16, int ts, int N, int nacc, int ldst, int depth, int reps, int blocks,
                       long long* out_dev, lrs_stream_t stream);

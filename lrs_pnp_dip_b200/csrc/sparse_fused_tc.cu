@@ -28,8 +28,10 @@
 // Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      MMA issuer (whole warp runs the loop, one elected lane issues)
 //   warp 1      TMEM allocator
-//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).., column half (w-4)/4 of every chunk
+//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and column group (w-4)/4 of every 64-column chunk
+//               (= 32 pixels of its patch).  NEPI = 16 (16 columns per thread) is supported but measured slower.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -41,16 +43,22 @@ namespace {
 
 constexpr int KATOMS = 256;
 constexpr int TILE = 128;
-constexpr int NTHREADS = 384;
-constexpr uint32_t COL_ALPHA = 0;    // [0,256)   fp32 alpha / GEMM-B accumulator
-constexpr uint32_t COL_ACC = 256;    // [256,320) alpha1 D1 + alpha2 D1 ; [320,384) alpha1 D2
+constexpr int NEPI = 8;                        // epilogue warps (8 measured faster than 16: the epilogue is issue-bound)
+constexpr int NCG = NEPI / 4;                  // column groups per TMEM lane quarter
+constexpr int CW = 64 / NCG;                   // columns (of a 64-column chunk) and pixels per epilogue thread
+constexpr int QPT = CW / 16;                   // 16-pixel residual quarters per epilogue thread
+constexpr int FIRST_EPI = (NEPI == 8) ? 4 : 2; // first epilogue warp (keeps warp % 4 == TMEM lane quarter)
+constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
+constexpr int NCHUNK = 4;                      // soft-threshold / GEMM-A pipeline: 4 chunks of 64 atoms
+constexpr uint32_t COL_ALPHA = 0;    // [0,256)   fp32 state / GEMM-B accumulator
+constexpr uint32_t COL_ACC = 256;    // [256,320) a1 D1 + a2 D1 ; [320,384) a1 D2
 constexpr uint32_t COL_STG0 = 384;   // staging buffers: piece 1 in [+0,+32), piece 2 in [+32,+64)
 constexpr uint32_t COL_STG1 = 448;   //   buffer 0 also carries the residual pieces between GEMM-A and GEMM-B
 // The state kept in TMEM is at = a * alpha' (alpha' = alpha / 2^ex, the patch-normalised coefficients), so that the
 // residual operand r = m .* (y' - D alpha') is O(1) whatever the step constant a is:
 //     at <- soft(at + r D, lambda' / 2),      D alpha' = (D at) / a
 // (soft is positively homogeneous: a * soft(g, T) = soft(a g, a T), and a T = lambda / 2).
-constexpr float S_ALPHA = 4.0f;      // state pieces    = fp16(4 at)
+constexpr float S_ALPHA = 1.0f;      // state pieces    = fp16(at)
 constexpr float S_D = 4.0f;          // D pieces        = fp16(4 D)
 constexpr float S_R = 0.25f;         // residual pieces = fp16(r / 4)  (S_R * S_D = 1: GEMM-B lands in the state's units)
 
@@ -60,15 +68,18 @@ constexpr uint32_t D_SMEM_BYTES = 64 * 1024;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 
 struct __align__(8) Shared {
-    uint64_t bar_R, bar_B, bar_S[4], bar_A[4];
+    uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in TMEM        (4 warps)
+    uint64_t bar_B;           // MMA -> epilogue: GEMM-B complete, state accumulators final               (commit)
+    uint64_t bar_S[NCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
+    uint64_t bar_A[NCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
     uint32_t tmem_base;
-    float xmax[2][TILE];      // per-patch partial max |y| of the two column halves
-    float xsum[2][TILE];      // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
+    float xmax[4][TILE];      // per-patch partial max |y| of the four pixel quarters
+    float xsum[4][TILE];      // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
     uint32_t xrow[TILE];      // validity bits of window column 0 (pixels 0..7)
     float rn[64];             // ||D[i,:]||^2
 };
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory"); }
 
 __device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -81,6 +92,26 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p1, uin
     p2 = pack_h2(l);
 }
 
+template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t a, uint32_t* r) {
+    if constexpr (N == 8) tmem_ld8(a, r);
+    else if constexpr (N == 16) tmem_ld16(a, r);
+    else tmem_ld32(a, r);
+}
+template <int N> __device__ __forceinline__ void tmem_stN(uint32_t a, const uint32_t* r) {
+    if constexpr (N == 8) tmem_st8(a, r);
+    else if constexpr (N == 16) tmem_st16(a, r);
+    else tmem_st32(a, r);
+}
+
+// Debug timing (LRS_TC_TIMING=1): cycles block 0 spends waiting at each barrier, summed over the run.
+//   [0] total MMA-warp cycles  [1..4] wait bar_R[ks]  [5..8] wait bar_S[j]  [10] MMA iterations
+//   [16] total epilogue (warp 2) cycles [17] wait bar_A[last] [18] wait bar_B [19],[20] wait bar_A[0],[1]
+//   [21] residual phase [22] soft phase [23] tile prologue [24] final epilogue
+__device__ unsigned long long g_tc_timing[32];
+
+#define TSTAMP() (DBG ? clock64() : 0ll)
+
+template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
@@ -110,10 +141,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         sh.rn[tid] = s;
     }
     if (tid == 0) {
-        mbar_init(&sh.bar_R, 8);
         mbar_init(&sh.bar_B, 1);
-        for (int j = 0; j < 4; ++j) {
-            mbar_init(&sh.bar_S[j], 8);
+        for (int j = 0; j < 4; ++j) mbar_init(&sh.bar_R[j], 4);
+        for (int j = 0; j < NCHUNK; ++j) {
+            mbar_init(&sh.bar_S[j], NEPI);
             mbar_init(&sh.bar_A[j], 1);
         }
         mbar_fence_init();
@@ -139,29 +170,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         //         groups SBO = D_SI apart; k-step covers atom groups 2g, 2g+1.
         const uint64_t descA0 = make_smem_desc(dbase, /*lbo=*/D_SK, /*sbo=*/D_SI);
         uint32_t gi = 0;
+        long long dbg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const long long t_begin = TSTAMP();
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
-                // ---- GEMM-B: alpha += r D ----
-                mbar_wait(&sh.bar_R, par);
-                tc_fence_after();
+                // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int kk = 0; kk < 4; ++kk) {
+                    // quarters become ready in the order the epilogue threads produce them: 0,2,1,3 when a thread
+                    // owns two consecutive quarters
+                    const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;
+                    long long w0 = TSTAMP();
+                    mbar_wait(&sh.bar_R[ks], par);
+                    if (DBG) dbg[1 + kk] += clock64() - w0;
+                    tc_fence_after();
                     const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI) >> 4);
                     const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI) >> 4);
                     const uint32_t r1 = tbase + COL_STG0 + 8 * ks, r2 = tbase + COL_STG0 + 32 + 8 * ks;
                     if (leader) {
-                        mma_f16_ts(tbase + COL_ALPHA, r1, d1, idescB, !(it == 0 && ks == 0));
+                        mma_f16_ts(tbase + COL_ALPHA, r1, d1, idescB, !(it == 0 && kk == 0));
                         mma_f16_ts(tbase + COL_ALPHA, r2, d1, idescB, true);
                         mma_f16_ts(tbase + COL_ALPHA, r1, d2, idescB, true);
                     }
+                    __syncwarp();
                 }
                 if (leader) mma_commit(&sh.bar_B);
                 __syncwarp();
-                // ---- GEMM-A: Da = alpha D^T, chunk by chunk as the soft-threshold epilogue releases them ----
+                // ---- GEMM-A: Da = state D^T, chunk by chunk as the soft-threshold epilogue releases them ----
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < NCHUNK; ++j) {
+                    long long w1 = TSTAMP();
                     mbar_wait(&sh.bar_S[j], par);
+                    if (DBG) dbg[5 + j] += clock64() - w1;
                     tc_fence_after();
                     const uint32_t stg = tbase + ((j & 1) ? COL_STG1 : COL_STG0);
 #pragma unroll
@@ -172,32 +213,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                             mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);               // a2 D1
                         }
                     }
-                    if (j != 2 && leader) mma_commit(&sh.bar_A[j]);
+                    if (j != NCHUNK - 2 && leader) mma_commit(&sh.bar_A[j]);   // nobody waits for chunk NCHUNK-2
                     __syncwarp();
                 }
+                if (DBG) dbg[10] += 1;
             }
         }
-    } else if (warp >= 4) {
+        if (DBG && blockIdx.x == 0 && leader) {
+            g_tc_timing[0] = clock64() - t_begin;
+            for (int i = 1; i < 11; ++i) g_tc_timing[i] = dbg[i];
+        }
+    } else if (warp >= FIRST_EPI) {
         // ================================ epilogue warps ================================
-        const int q = warp & 3;               // TMEM lane quarter
-        const int h = (warp - 4) >> 2;        // column half
-        const int m = q * 32 + lane;          // patch within the tile = TMEM lane
+        const int q = warp & 3;                     // TMEM lane quarter (hardware: warp % 4)
+        const int cg = (warp - FIRST_EPI) >> 2;     // column group: CW of every 64 columns, pixels [CW*cg, CW*cg+CW)
+        const int m = q * 32 + lane;                // patch within the tile = TMEM lane
         const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
         const int64_t nR = prm.g.row.n, C = prm.g.C;
         uint32_t gi = 0;
+        long long ed[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const long long e_begin = TSTAMP();
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // ---- tile prologue: gather my 32 pixels (window columns 4h..4h+3), mask, step constant, scale ----
+            const long long tp0 = TSTAMP();
+            // ---- tile prologue: gather my CW pixels (window columns CW/8*cg ..), mask, step constant, scale ----
             const int64_t pi = tile * TILE + m;
             const bool valid = pi < total;
             const int64_t p = prm.p_begin + (valid ? pi : total - 1);
             const int64_t ci = p / nR, ri = p - ci * nR;
             const int64_t rs = prm.g.row.start(ri), cs = prm.g.col.start(ci);
-            float ysc[32];
+            float ysc[CW];
             uint32_t mbits = 0;
             float amax = 0.f, nsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int64_t src = (rs + (c & 7)) * C + cs + 4 * h + (c >> 3);
+            for (int c = 0; c < CW; ++c) {
+                const int64_t src = (rs + (c & 7)) * C + cs + (CW / 8) * cg + (c >> 3);
                 float v = __ldg(prm.X + src);
                 if (prm.L) v = __fadd_rn(v, __fdiv_rn(__ldg(prm.L + src), prm.mu1));
                 const bool ok = __ldg(prm.Yobs + src) != 0.0f;
@@ -205,18 +254,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 if (ok) {
                     mbits |= 1u << c;
                     amax = fmaxf(amax, fabsf(v));
-                    nsum += sh.rn[32 * h + c];
+                    nsum += sh.rn[CW * cg + c];
                 }
             }
-            sh.xmax[h][m] = amax;
-            sh.xsum[h][m] = nsum;
-            if (h == 0) sh.xrow[m] = mbits & 0xFFu;
+            sh.xmax[cg][m] = amax;
+            sh.xsum[cg][m] = nsum;
+            if (cg == 0) sh.xrow[m] = mbits & 0xFFu;
             epi_barrier();
-            amax = fmaxf(sh.xmax[0][m], sh.xmax[1][m]);
-            float a;
+            float a = 0.f;
+            amax = 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < NCG; ++g2) {
+                amax = fmaxf(amax, sh.xmax[g2][m]);
+                a += sh.xsum[g2][m];
+            }
+            a *= 4.0f;                                              // 4 ||H||_F^2 (main_LRS_PnP_DIP_pro.py:190)
             if (prm.a_patch) a = __ldg(prm.a_patch + p);
             else if (prm.a_table) a = __ldg(prm.a_table + sh.xrow[m]);
-            else a = 4.0f * (sh.xsum[0][m] + sh.xsum[1][m]);
             epi_barrier();  // exchange buffers are free for the next tile
             const bool ok_a = a > 0.0f;
             const float inv_a = ok_a ? __fdiv_rn(1.0f, a) : 0.0f;
@@ -227,54 +281,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             const float c1 = S_R * dn;                            // y -> scaled residual units
             const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= S_ALPHA S_D a D alpha') -> scaled residual units
 #pragma unroll
-            for (int c = 0; c < 32; ++c) ysc[c] *= c1;
+            for (int c = 0; c < CW; ++c) ysc[c] *= c1;
+            if (DBG) ed[7] += clock64() - tp0;
 
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
-                // ---- residual: r = m .* (y - D alpha) / a  -> fp16 pieces in staging buffer 0 ----
-                {
-                    uint32_t p1[16], p2[16];
+                const long long tr0 = TSTAMP();
+                // ---- residual: r = m .* (y' - D at / a) -> fp16 pieces in staging buffer 0, one 16-pixel quarter at a
+                //      time so that GEMM-B starts on the first quarters while the others are being computed ----
+                if (it > 0) {
+                    mbar_wait(&sh.bar_A[NCHUNK - 1], par ^ 1);
+                    if (DBG) ed[1] += clock64() - tr0;
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int qq = 0; qq < QPT; ++qq) {
+                    const int ks = QPT * cg + qq;            // pixel quarter = GEMM-B k-step
+                    uint32_t p1[8], p2[8];
                     if (it > 0) {
-                        uint32_t a0[32], a1[32];
-                        mbar_wait(&sh.bar_A[3], par ^ 1);
-                        tc_fence_after();
-                        tmem_ld32(lane_addr + COL_ACC + 32 * h, a0);
-                        tmem_ld32(lane_addr + COL_ACC + 64 + 32 * h, a1);
+                        uint32_t a0[16], a1[16];
+                        tmem_ld16(lane_addr + COL_ACC + 16 * ks, a0);
+                        tmem_ld16(lane_addr + COL_ACC + 64 + 16 * ks, a1);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
+                        for (int c = 0; c < 8; ++c) {
+                            const int e = 16 * qq + 2 * c;
                             float s0 = __uint_as_float(a0[2 * c]) + __uint_as_float(a1[2 * c]);
                             float s1 = __uint_as_float(a0[2 * c + 1]) + __uint_as_float(a1[2 * c + 1]);
-                            float r0 = ((mbits >> (2 * c)) & 1u) ? fmaf(-c2, s0, ysc[2 * c]) : 0.f;
-                            float r1 = ((mbits >> (2 * c + 1)) & 1u) ? fmaf(-c2, s1, ysc[2 * c + 1]) : 0.f;
+                            float r0 = ((mbits >> e) & 1u) ? fmaf(-c2, s0, ysc[e]) : 0.f;
+                            float r1 = ((mbits >> (e + 1)) & 1u) ? fmaf(-c2, s1, ysc[e + 1]) : 0.f;
                             split_pair(r0, r1, p1[c], p2[c]);
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            float r0 = ((mbits >> (2 * c)) & 1u) ? ysc[2 * c] : 0.f;
-                            float r1 = ((mbits >> (2 * c + 1)) & 1u) ? ysc[2 * c + 1] : 0.f;
+                        for (int c = 0; c < 8; ++c) {
+                            const int e = 16 * qq + 2 * c;
+                            float r0 = ((mbits >> e) & 1u) ? ysc[e] : 0.f;
+                            float r1 = ((mbits >> (e + 1)) & 1u) ? ysc[e + 1] : 0.f;
                             split_pair(r0, r1, p1[c], p2[c]);
                         }
                     }
-                    tmem_st16(lane_addr + COL_STG0 + 16 * h, p1);
-                    tmem_st16(lane_addr + COL_STG0 + 32 + 16 * h, p2);
+                    tmem_st8(lane_addr + COL_STG0 + 8 * ks, p1);
+                    tmem_st8(lane_addr + COL_STG0 + 32 + 8 * ks, p2);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.bar_R);
+                    if (lane == 0) mbar_arrive(&sh.bar_R[ks]);
                 }
-                // ---- soft threshold, 4 chunks of 64 atoms; my 32 columns of each ----
+                // ---- soft threshold, 4 chunks of 64 atoms; my CW columns of each.  The load of chunk j+1 is in
+                //      flight while chunk j is processed. ----
+                const long long ts0 = TSTAMP();
+                if (DBG) ed[5] += ts0 - tr0;
                 mbar_wait(&sh.bar_B, par);
+                if (DBG) ed[2] += clock64() - ts0;
                 tc_fence_after();
+                uint32_t ga[CW], gb[CW];
+                tmem_ldN<CW>(lane_addr + COL_ALPHA + CW * cg, ga);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t g[32], p1[16], p2[16];
-                    const uint32_t col = COL_ALPHA + 64 * j + 32 * h;
-                    tmem_ld32(lane_addr + col, g);
+                for (int j = 0; j < NCHUNK; ++j) {
+                    uint32_t* g = (j & 1) ? gb : ga;
+                    uint32_t* gn = (j & 1) ? ga : gb;
+                    uint32_t p1[CW / 2], p2[CW / 2];
+                    const uint32_t col = COL_ALPHA + 64 * j + CW * cg;
                     tmem_wait_ld();
+                    if (j + 1 < NCHUNK) tmem_ldN<CW>(lane_addr + col + 64, gn);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
+                    for (int c = 0; c < CW / 2; ++c) {
                         float x0 = soft_thr(__uint_as_float(g[2 * c]), Tn);
                         float x1 = soft_thr(__uint_as_float(g[2 * c + 1]), Tn);
                         g[2 * c] = __float_as_uint(x0);
@@ -282,35 +354,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                         split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
                     }
                     if (j >= 2) {  // staging buffer (j&1) is free once GEMM-A of chunk j-2 has completed
+                        const long long tw = TSTAMP();
                         mbar_wait(&sh.bar_A[j - 2], par);
+                        if (DBG) ed[3 + (j - 2)] += clock64() - tw;
                         tc_fence_after();
                     }
                     const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
-                    tmem_st32(lane_addr + col, g);
-                    tmem_st16(lane_addr + stg + 16 * h, p1);
-                    tmem_st16(lane_addr + stg + 32 + 16 * h, p2);
+                    tmem_stN<CW>(lane_addr + col, g);
+                    tmem_stN<CW / 2>(lane_addr + stg + (CW / 2) * cg, p1);
+                    tmem_stN<CW / 2>(lane_addr + stg + 32 + (CW / 2) * cg, p2);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.bar_S[j]);
                 }
+                if (DBG) ed[6] += clock64() - ts0;
             }
-            // ---- Phi_z = D alpha_final (main_LRS_PnP.py:294): my 32 pixels of my patch ----
+            const long long tf0 = TSTAMP();
+            // ---- Phi_z = D alpha_final (main_LRS_PnP.py:294): my CW pixels of my patch ----
             {
-                uint32_t a0[32], a1[32];
-                mbar_wait(&sh.bar_A[3], (gi - 1) & 1);
+                uint32_t a0[CW], a1[CW];
+                mbar_wait(&sh.bar_A[NCHUNK - 1], (gi - 1) & 1);
                 tc_fence_after();
-                tmem_ld32(lane_addr + COL_ACC + 32 * h, a0);
-                tmem_ld32(lane_addr + COL_ACC + 64 + 32 * h, a1);
+                tmem_ldN<CW>(lane_addr + COL_ACC + CW * cg, a0);
+                tmem_ldN<CW>(lane_addr + COL_ACC + 64 + CW * cg, a1);
                 tmem_wait_ld();
                 tc_fence_before();   // order these loads before the next tile's MMAs (via bar_R)
                 const float sc = up * inv_a / (S_ALPHA * S_D);
                 if (valid) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        prm.phi[(int64_t)(32 * h + c) * total + pi] = (__uint_as_float(a0[c]) + __uint_as_float(a1[c])) * sc;
+                    for (int c = 0; c < CW; ++c)
+                        prm.phi[(int64_t)(CW * cg + c) * total + pi] = (__uint_as_float(a0[c]) + __uint_as_float(a1[c])) * sc;
                 }
             }
+            if (DBG) ed[8] += clock64() - tf0;
+        }
+        if (DBG && blockIdx.x == 0 && warp == FIRST_EPI && lane == 0) {
+            g_tc_timing[16] = clock64() - e_begin;
+            for (int i = 1; i < 9; ++i) g_tc_timing[16 + i] = ed[i];
         }
     }
     tc_fence_before();
@@ -332,15 +413,26 @@ int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     if (!sparse_fused_tc_supported(prm, K)) return fail_arg(fn, "tcgen05 engine needs K = 256, Nit >= 1 and an sm_100 device");
     const size_t smem = D_SMEM_BYTES + sizeof(Shared);
-    int rc = check_cuda(fn, cudaFuncSetAttribute(sparse_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
+    auto kern = dbg ? sparse_fused_tc_kernel<true> : sparse_fused_tc_kernel<false>;
+    int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
     int sms = device_sm_count();
     if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
     int64_t ntiles = (prm.p_end - prm.p_begin + TILE - 1) / TILE;
     unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    sparse_fused_tc_kernel<<<grid, NTHREADS, smem, st>>>(prm);
+    kern<<<grid, NTHREADS, smem, st>>>(prm);
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
 
+int tc_timing_read(unsigned long long* out32) {
+    return check_cuda("lrs_tc_timing_read", cudaMemcpyFromSymbol(out32, g_tc_timing, sizeof(unsigned long long) * 32));
+}
+
 }  // namespace lrs
+
+extern "C" int lrs_tc_timing_read(unsigned long long* out32_host) {
+    if (!out32_host) return lrs::fail_arg("lrs_tc_timing_read", "null pointer");
+    return lrs::tc_timing_read(out32_host);
+}
