@@ -243,11 +243,15 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     launches0 = L.lrs_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:          # ncu --profile-from-start off: capture the timed steps only
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         sol.step()
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     launches = int(L.lrs_launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -346,6 +350,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

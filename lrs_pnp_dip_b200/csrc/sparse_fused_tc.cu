@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 if (valid) {
 #pragma unroll
                     for (int c = 0; c < CW; ++c)
-                        prm.phi[(int64_t)(CW * cg + c) * total + pi] = (__uint_as_float(a0[c]) + __uint_as_float(a1[c])) * sc;
+                        __stcs(prm.phi + (int64_t)(CW * cg + c) * total + pi,
+                               (__uint_as_float(a0[c]) + __uint_as_float(a1[c])) * sc);   // streaming: keep the cube in L2
                 }
             }
             if (DBG) ed[8] += clock64() - tf0;
