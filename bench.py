@@ -211,6 +211,9 @@ def run_ours(args, rank, world, local_rank):
     Yl = np.ascontiguousarray(Y[st.row_slice])
     Ml = np.ascontiguousarray(np.repeat(pm[st.row_slice].astype(np.float32)[:, None], C, axis=1))
     P_local = (st.b - st.a) * (C - BB + 1)
+    if world > 1:
+        del Y          # every rank generated the same seeded cube; keep only the stripe
+        Y = None
 
     sol = lrs.LRSPnP(torch.from_numpy(Yl), torch.from_numpy(Ml), torch.from_numpy(D), prm, engine=args.engine,
                      stripe=st if world > 1 else None, device=dev)
