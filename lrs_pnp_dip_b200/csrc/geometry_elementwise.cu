@@ -78,7 +78,31 @@ __global__ void im2col_kernel(Geom g, const float* __restrict__ X, const float* 
 // 32x32 tile, threads run along r while gathering (coalesced along p), transposed through shared
 // memory so the store runs along c.
 // ------------------------------------------------------------------------------------------------
-__global__ void col2im_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
+// Sum, in ascending row-start order, of the regular row starts [rlo, rhi] (+ the appended last start) of one column
+// start.  `pc` points at blocks[(bb*j)*P + ci*nR]; consecutive row starts are one pointer step apart, so the walk
+// costs an add per load (the kernel is instruction-issue bound otherwise: measured 56 instructions per load).
+__device__ __forceinline__ float col2im_column(const Geom& g, const float* __restrict__ pc, int64_t r, int64_t rlo,
+                                               int64_t nreg, bool rapp, float sum) {
+    const int64_t step = 1 - (int64_t)g.row.s * g.P;
+    const float* pr = pc + (r - rlo * g.row.s) * g.P + rlo;
+    int64_t b = 0;
+    for (; b + 8 <= nreg; b += 8) {  // 8 independent loads in flight, then the adds in patch order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(pr + u * step);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum = __fadd_rn(sum, v[u]);
+        pr += 8 * step;
+    }
+    for (; b < nreg; ++b) {
+        sum = __fadd_rn(sum, __ldg(pr));
+        pr += step;
+    }
+    if (rapp) sum = __fadd_rn(sum, __ldg(pc + (r - g.row.last) * g.P + g.row.n_reg));
+    return sum;
+}
+
+__global__ void __launch_bounds__(256, 6) col2im_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
     __shared__ float tile[32][33];
     int64_t r0 = blockIdx.x * 32LL, c0 = blockIdx.y * 32LL;
     int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (32, 8)
@@ -90,17 +114,17 @@ __global__ void col2im_kernel(Geom g, const float* __restrict__ blocks, float* _
             bool rapp, capp;
             g.row.cover(r, rlo, rhi, rapp);
             g.col.cover(c, clo, chi, capp);
-            int64_t nci = (chi - clo + 1 > 0 ? chi - clo + 1 : 0) + (capp ? 1 : 0);
-            int64_t nri = (rhi - rlo + 1 > 0 ? rhi - rlo + 1 : 0) + (rapp ? 1 : 0);
-            for (int64_t a = 0; a < nci; ++a) {
-                int64_t ci = (capp && a == nci - 1) ? g.col.n_reg : clo + a;
-                int j = (int)(c - g.col.start(ci));
-                for (int64_t b = 0; b < nri; ++b) {
-                    int64_t ri = (rapp && b == nri - 1) ? g.row.n_reg : rlo + b;
-                    int i = (int)(r - g.row.start(ri));
-                    sum = __fadd_rn(sum, __ldg(blocks + (int64_t)(i + g.bb * j) * g.P + ci * g.row.n + ri));
-                }
+            const int64_t nreg = rhi - rlo + 1 > 0 ? rhi - rlo + 1 : 0;
+            // regular column starts ci = clo..chi: j = c - ci*s; next ci: j -= s
+            const float* pc = blocks + ((int64_t)g.bb * (c - clo * g.col.s)) * g.P + clo * g.row.n;
+            const int64_t cstep = g.row.n - (int64_t)g.bb * g.col.s * g.P;
+            for (int64_t ci = clo; ci <= chi; ++ci) {
+                sum = col2im_column(g, pc, r, rlo, nreg, rapp, sum);
+                pc += cstep;
             }
+            if (capp)
+                sum = col2im_column(g, blocks + ((int64_t)g.bb * (c - g.col.last)) * g.P + g.col.n_reg * g.row.n, r, rlo, nreg,
+                                    rapp, sum);
         }
         tile[cc][tx] = sum;
     }
@@ -172,9 +196,10 @@ __global__ void admm_update_kernel(Geom g, const float* __restrict__ Y, const fl
                                    const float* __restrict__ IM, const float* __restrict__ U, float* __restrict__ lam1,
                                    float* __restrict__ lam2, float* __restrict__ Xo, float gamma, float mu1, float mu2,
                                    int64_t rows, int64_t row_offset) {
-    int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= rows * g.C) return;
-    int64_t r = idx / g.C, c = idx - r * g.C;
+    const int64_t r = blockIdx.x;                                        // one unfolded row per block row
+    const int64_t c = blockIdx.y * (int64_t)blockDim.x + threadIdx.x;    // bands along the threads (coalesced)
+    if (r >= rows || c >= g.C) return;
+    const int64_t idx = r * g.C + c;
     int W = g.row.count(r + row_offset) * g.col.count(c);
     float l1 = lam1[idx], l2 = lam2[idx], im = IM[idx], u = U[idx];
     float l1s = 0.0f;
@@ -321,8 +346,11 @@ int lrs_admm_update_f32(const float* Y_dev, const float* MtM_dev, const float* i
     if (rows == 0) return LRS_OK;
     if (!Y_dev || !MtM_dev || !imout_dev || !U_dev || !lam1_dev || !lam2_dev || !X_out_dev)
         return fail_arg("lrs_admm_update_f32", "null pointer");
-    admm_update_kernel<<<blocks_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(
-        g, Y_dev, MtM_dev, imout_dev, U_dev, lam1_dev, lam2_dev, X_out_dev, gamma, mu_1, mu_2, rows, row_offset);
+    const int threads = C >= 256 ? 256 : (int)((C + 31) / 32 * 32);
+    dim3 grid((unsigned)rows, blocks_for(C, threads));
+    if (rows > 2147483647LL || grid.y > 65535) return fail_arg("lrs_admm_update_f32", "matrix too large");
+    admm_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(g, Y_dev, MtM_dev, imout_dev, U_dev, lam1_dev, lam2_dev,
+                                                                  X_out_dev, gamma, mu_1, mu_2, rows, row_offset);
     LRS_CHECK_LAUNCH("lrs_admm_update_f32");
     return LRS_OK;
 }

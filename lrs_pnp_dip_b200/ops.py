@@ -178,6 +178,26 @@ def row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
     window element (i, j) is valid iff unfolded row r+i is observed).  bb = 8 → 256 entries."""
     n, K = D.shape
     assert n == bb * bb
+    # The table depends on the dictionary only; the reference recomputes it per patch per outer iteration
+    # (main_LRS_PnP.py:134).  Cache per dictionary tensor (storage, version) so repeated calls reuse it.
+    Dd = D.double()
+    fingerprint = tuple(torch.stack([Dd.sum(), (Dd * Dd).sum(), Dd[0].sum(), Dd[:, 0].sum(), Dd[-1, -1]]).tolist())
+    key = (fingerprint, tuple(D.shape), str(D.device), bb, step)
+    hit = _TABLE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _row_pattern_table(D, bb, step)
+    if len(_TABLE_CACHE) > 16:
+        _TABLE_CACHE.clear()
+    _TABLE_CACHE[key] = out
+    return out
+
+
+_TABLE_CACHE: dict = {}
+
+
+def _row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
+    n, K = D.shape
     i_of_k = torch.arange(n, device=D.device) % bb
     bits = torch.arange(1 << bb, device=D.device)
     m = ((bits[:, None] >> i_of_k[None, :]) & 1).to(torch.float64)          # [2^bb, n]
