@@ -44,10 +44,14 @@ extern "C" {
 #define LRS_STEP_SPECTRAL 0 /* a = ||H||_2^2        main_LRS_PnP.py:134, ista.m:15 */
 #define LRS_STEP_FROB4 1    /* a = 4*||H||_F^2      main_LRS_PnP_DIP_pro.py:190     */
 
+#define LRS_DENOISE_SOFT 0
+#define LRS_DENOISE_NLM 1
+#define LRS_DENOISE_IDENTITY 2
+
 /* engines of lrs_sparse_step_fused_f32 */
 #define LRS_ENGINE_AUTO 0
 #define LRS_ENGINE_SIMT 1   /* fp32 FFMA kernel (any K multiple of 16 up to 256)          */
-#define LRS_ENGINE_TC 2     /* tcgen05/TMEM 3xTF32 kernel (n = 64, K = 256)               */
+#define LRS_ENGINE_TC 2     /* tcgen05/TMEM kernel, 3-pass fp16 split (n = 64, K = 256)   */
 
 typedef void* lrs_stream_t;
 
@@ -103,6 +107,13 @@ size_t lrs_ista_workspace_bytes(int n, int K, int64_t P);
 int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
                       float lambda_ista, int Nit, int n, int K, int64_t P, float* coefs_dev, float* phi_z_dev,
                       void* workspace_dev, size_t workspace_bytes, lrs_stream_t stream);
+
+/* Plug-and-play variant: the same iteration with the proximal step replaced by a denoiser of the K x 1 gradient-step
+ * vector — LRS_DENOISE_SOFT soft(g, T) (ista.m:23); LRS_DENOISE_NLM NLmeansfilter(g, 3, 3, h_scale*T)
+ * (pnp_ista.m:30, NLmeansfilter.m:1-91; h_scale = 0.1 in the MATLAB file); LRS_DENOISE_IDENTITY none. */
+int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
+                     float lambda_ista, int Nit, int n, int K, int64_t P, int denoiser, float h_scale, float* coefs_dev,
+                     float* phi_z_dev, void* workspace_dev, size_t workspace_bytes, lrs_stream_t stream);
 
 /* ---- fused sparse step on the implicit patch set (bb = 8) ------------------------------------ */
 /* phi_z[64,P] for all patches of V = X + L/mu_1, mask taken from Yobs != 0 (main_LRS_PnP.py:244,

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblrs_pnp.so")
 STEP_SPECTRAL, STEP_FROB4 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}
+DENOISERS = {"soft": 0, "nlm": 1, "identity": 2}
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -39,6 +40,7 @@ SIGNATURES = {
     "lrs_step_frob4_f32": (_int, [_p, _p, _int, _int, _i64, _p, _p]),
     "lrs_ista_workspace_bytes": (C.c_size_t, [_int, _int, _i64]),
     "lrs_ista_soft_f32": (_int, [_p, _p, _p, _p, _f, _int, _int, _int, _i64, _p, _p, _p, C.c_size_t, _p]),
+    "lrs_ista_pnp_f32": (_int, [_p, _p, _p, _p, _f, _int, _int, _int, _i64, _int, _f, _p, _p, _p, C.c_size_t, _p]),
     "lrs_sparse_step_fused_f32": (_int, [_p, _p, _f, _p, _p, _int, _p, _p, _f, _int, _i64, _i64, _int, _int, _i64,
                                          _i64, _p, _int, _p]),
     "lrs_admm_update_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i64, _i64, _i64, _i64, _int, _int, _p]),

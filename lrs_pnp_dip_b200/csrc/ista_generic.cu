@@ -31,6 +31,14 @@ struct EpiGradient {  // c = D^T Rm  ->  A = soft(A + c, T)
         A[o] = soft_thr(A[o] + acc, T[p]);
     }
 };
+struct EpiGradientPlain {  // c = D^T Rm  ->  G = A + c   (input of a plug-and-play denoiser; identity when G == A buffer)
+    const float* A;
+    float* G;
+    __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const {
+        int64_t o = m * ld + p;
+        G[o] = A[o] + acc;
+    }
+};
 struct EpiStore {
     float* out;
     __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const { out[m * ld + p] = acc; }
@@ -125,6 +133,48 @@ __global__ void ista_prepare_kernel(const float* __restrict__ a, float lambda, i
     T[p] = ok ? __fdiv_rn(lambda, __fmul_rn(2.0f, av)) : 0.0f;  // T = lambda/(2a), ista.m:17
 }
 
+// 1-D non-local means along the atom axis of G [K,P] (one column per patch): NLmeansfilter.m:18-91 on a K x 1 input
+// with search radius 3 and patch radius 3 (pnp_ista.m:30), h = h_scale * T[p].  The symmetric padding (:24) makes
+// the 7 window columns identical, so the 7x7 weighted distance reduces to 7 taps (row sums of make_kernel, :80-91).
+__global__ void nlm_column_kernel(const float* __restrict__ G, const float* __restrict__ T, float h_scale, int K, int64_t P,
+                                  float* __restrict__ out) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (p >= P) return;
+    const float kw[7] = {1.0f / 21.0f, 4.0f / 35.0f, 71.0f / 315.0f, 71.0f / 315.0f, 71.0f / 315.0f, 4.0f / 35.0f, 1.0f / 21.0f};
+    float x[13];  // G[k-6 .. k+6] with symmetric (edge-including mirror) extension
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {
+        int idx = k - 6 + u;
+        if (idx < 0) idx = -idx - 1;
+        if (idx >= K) idx = 2 * K - 1 - idx;
+        idx = idx < 0 ? 0 : (idx >= K ? K - 1 : idx);
+        x[u] = __ldg(G + (int64_t)idx * P + p);
+    }
+    const float h = h_scale * T[p];
+    const float inv_h2 = h > 0.f ? 1.0f / (h * h) : 0.f;
+    float wmax = 0.f, avg = 0.f, sw = 0.f;
+#pragma unroll
+    for (int dr = -3; dr <= 3; ++dr) {
+        if (dr == 0) continue;
+        const int r = k + dr;
+        if (r < 0 || r >= K) continue;  // the search window is clipped to the real column (:46-49)
+        float d = 0.f;
+#pragma unroll
+        for (int u = -3; u <= 3; ++u) {
+            float e = x[6 + u] - x[6 + dr + u];
+            d = fmaf(kw[u + 3] * e, e, d);
+        }
+        float w = h > 0.f ? __expf(-d * inv_h2) : (d == 0.f ? 1.f : 0.f);
+        wmax = fmaxf(wmax, w);
+        sw += w;
+        avg = fmaf(w, x[6 + dr], avg);
+    }
+    avg = fmaf(wmax, x[6], avg);
+    sw += wmax;
+    out[(int64_t)k * P + p] = sw > 0.f ? avg / sw : x[6];
+}
+
 template <bool TRANS_A, class ALoad, class Epi>
 static int launch_gemm(const char* fn, ALoad al, const float* B, int64_t M, int64_t N, int64_t Kd, Epi epi,
                        cudaStream_t st) {
@@ -158,15 +208,24 @@ extern "C" {
 
 size_t lrs_ista_workspace_bytes(int n, int K, int64_t P) {
     if (n <= 0 || K <= 0 || P < 0) return 0;
-    // coefs [K,P] + residual [n,P] + inv_a [P] + T [P], each 256-byte aligned
+    // coefs [K,P] + denoiser input [K,P] + residual [n,P] + inv_a [P] + T [P], each 256-byte aligned
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    return al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4);
+    return 2 * al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4);
 }
 
 int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
                       float lambda_ista, int Nit, int n, int K, int64_t P, float* coefs_dev, float* phi_z_dev,
                       void* workspace_dev, size_t workspace_bytes, lrs_stream_t stream) {
-    const char* fn = "lrs_ista_soft_f32";
+    return lrs_ista_pnp_f32(blocks_dev, blocks_copy_dev, D_dev, a_dev, lambda_ista, Nit, n, K, P, LRS_DENOISE_SOFT, 1.0f,
+                            coefs_dev, phi_z_dev, workspace_dev, workspace_bytes, stream);
+}
+
+int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
+                     float lambda_ista, int Nit, int n, int K, int64_t P, int denoiser, float h_scale, float* coefs_dev,
+                     float* phi_z_dev, void* workspace_dev, size_t workspace_bytes, lrs_stream_t stream) {
+    const char* fn = "lrs_ista_pnp_f32";
+    if (denoiser != LRS_DENOISE_SOFT && denoiser != LRS_DENOISE_NLM && denoiser != LRS_DENOISE_IDENTITY)
+        return fail_arg(fn, "unknown denoiser");
     if (n <= 0 || K <= 0 || P < 0 || Nit < 0) return fail_arg(fn, "bad shape");
     if (!blocks_dev || !blocks_copy_dev || !D_dev || !a_dev) return fail_arg(fn, "null pointer");
     if (P == 0) return LRS_OK;
@@ -178,6 +237,8 @@ int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, con
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     char* w = (char*)workspace_dev;
     float* A = (float*)w;
+    w += al((size_t)K * P * 4);
+    float* Gd = (float*)w;
     w += al((size_t)K * P * 4);
     float* Rm = (float*)w;
     w += al((size_t)n * P * 4);
@@ -192,7 +253,19 @@ int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, con
     for (int it = 0; it < Nit; ++it) {
         rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiResidual{blocks_dev, blocks_copy_dev, inv_a, Rm}, st);
         if (rc != LRS_OK) return rc;
-        rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradient{T, A}, st);
+        if (denoiser == LRS_DENOISE_SOFT) {
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradient{T, A}, st);
+        } else if (denoiser == LRS_DENOISE_IDENTITY) {
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, A}, st);
+        } else {
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, Gd}, st);
+            if (rc != LRS_OK) return rc;
+            dim3 grid((unsigned)((P + 127) / 128), (unsigned)K);
+            if (K > 65535) return fail_arg(fn, "K too large for the NLM denoiser");
+            nlm_column_kernel<<<grid, 128, 0, st>>>(Gd, T, h_scale, K, P, A);
+            note_launch();
+            rc = check_cuda(fn, cudaGetLastError());
+        }
         if (rc != LRS_OK) return rc;
     }
     if (phi_z_dev) {

@@ -212,9 +212,10 @@ def _row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
 
 # ------------------------------------------------------------------ ista
 def ista_batched(blocks: torch.Tensor, blocks_copy: torch.Tensor, D: torch.Tensor, a: torch.Tensor, lambda_ista: float,
-                 Nit: int, want_coefs: bool = False, want_phi: bool = True):
+                 Nit: int, want_coefs: bool = False, want_phi: bool = True, denoiser: str = "soft", h_scale: float = 0.1):
     """All patches at once (explicit patch matrices, any n / K / P).  Returns (coefs [K,P] | None,
-    phi_z [n,P] | None).  Replaces the jj loop main_LRS_PnP.py:270-303."""
+    phi_z [n,P] | None).  Replaces the jj loop main_LRS_PnP.py:270-303.  ``denoiser``: 'soft' (ista.m:23),
+    'nlm' (NLmeansfilter(g,3,3,h_scale*T), pnp_ista.m:30) or 'identity'."""
     n, P = blocks.shape
     K = D.shape[1]
     L = lib()
@@ -222,18 +223,20 @@ def ista_batched(blocks: torch.Tensor, blocks_copy: torch.Tensor, D: torch.Tenso
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=blocks.device)
     coefs = torch.empty((K, P), dtype=torch.float32, device=blocks.device) if want_coefs else None
     phi = torch.empty((n, P), dtype=torch.float32, device=blocks.device) if want_phi else None
-    check(L.lrs_ista_soft_f32(ptr(blocks), ptr(blocks_copy), ptr(D), ptr(a), float(lambda_ista), int(Nit), n, K, P,
-                              ptr(coefs), ptr(phi), ptr(ws), ws_bytes, stream_ptr()), "lrs_ista_soft_f32")
+    if denoiser not in _lib.DENOISERS:
+        raise ValueError(f"unknown denoiser {denoiser!r}")
+    check(L.lrs_ista_pnp_f32(ptr(blocks), ptr(blocks_copy), ptr(D), ptr(a), float(lambda_ista), int(Nit), n, K, P,
+                             _lib.DENOISERS[denoiser], float(h_scale), ptr(coefs), ptr(phi), ptr(ws), ws_bytes,
+                             stream_ptr()), "lrs_ista_pnp_f32")
     return coefs, phi
 
 
-def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "spectral"):
-    """main_LRS_PnP.py:131-149 / main_LRS_PnP_DIP_pro.py:188-201 / ista.m:1-24.
+def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "spectral", h_scale: float = 0.1):
+    """main_LRS_PnP.py:131-149 / main_LRS_PnP_DIP_pro.py:188-201 / ista.m:1-24 / pnp_ista.m:1-32.
     ``alpha`` is ignored and recomputed exactly as the reference does (``step='spectral'``:
-    ‖H‖₂² ; ``'frob4'``: 4‖H‖_F²).  ``denoiser='soft'`` is the MATLAB twin's soft(g, T)
-    (ista.m:23) — the NLM plug-in of the Python scripts is not provided."""
-    if denoiser != "soft":
-        raise NotImplementedError("only the soft-threshold denoiser (ista.m:23) is implemented on the device")
+    ‖H‖₂² ; ``'frob4'``: 4‖H‖_F²).  ``denoiser='soft'`` is the MATLAB twin's soft(g, T) (ista.m:23);
+    ``'nlm'`` is the in-repo MATLAB NLmeansfilter(g, 3, 3, h_scale*T) (pnp_ista.m:30) — the skimage
+    ``denoise_nl_means`` of the Python scripts is a different third-party algorithm and is not reproduced."""
     Hd, src, _ = _to_dev(H)
     yd, _, _ = _to_dev(y)
     yd = yd.reshape(-1, 1)
@@ -243,7 +246,8 @@ def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "
             a = torch.tensor([spectral_norm_sq(Hd)], dtype=torch.float32, device=Hd.device)
         else:
             a = step_constants(ones, Hd, step)
-        coefs, _ = ista_batched(yd, ones, Hd, a, lambda_ista, Nit, want_coefs=True, want_phi=False)
+        coefs, _ = ista_batched(yd, ones, Hd, a, lambda_ista, Nit, want_coefs=True, want_phi=False, denoiser=denoiser,
+                                h_scale=h_scale)
     return _back(coefs, src)
 
 

@@ -43,6 +43,8 @@ class Params:
     bb: int = 36
     slidingDis: int = 36
     step: str = "spectral"
+    denoiser: str = "soft"      # 'soft' (ista.m:23) | 'nlm' (pnp_ista.m:30, explicit engine only) | 'identity'
+    nlm_h_scale: float = 0.1    # h = nlm_h_scale * T
 
 
 # --------------------------------------------------------------------------------------------------
@@ -109,7 +111,7 @@ class SparseCoder:
             raise ValueError(f"dictionary has {self.n} rows, bb² = {prm.bb * prm.bb}")
         self.P = ops.patch_count(self.R, self.C, prm.bb, prm.slidingDis)
         self.engine = _lib.ENGINES[engine]
-        self.fused = prm.bb == 8 and self.K in FUSED_K
+        self.fused = prm.bb == 8 and self.K in FUSED_K and prm.denoiser == "soft"
         self.a_patch = self.a_table = self.blocks_copy = None
         if self.fused:
             if prm.step == "spectral":
@@ -135,7 +137,8 @@ class SparseCoder:
                                                   self.engine, stream_ptr()), "lrs_sparse_step_fused_f32")
             return phi
         blocks = ops.im2col(X, prm.bb, prm.slidingDis, lambda_1, prm.mu_1)
-        _, phi = ops.ista_batched(blocks, self.blocks_copy, self.D, self.a_patch, prm.lambda_ista, prm.Nit)
+        _, phi = ops.ista_batched(blocks, self.blocks_copy, self.D, self.a_patch, prm.lambda_ista, prm.Nit,
+                                  denoiser=prm.denoiser, h_scale=prm.nlm_h_scale)
         return phi
 
     def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:

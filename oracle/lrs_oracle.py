@@ -315,3 +315,60 @@ def psnr_ref(a: np.ndarray, b: np.ndarray) -> float:
 def mpsnr_ref(clean: np.ndarray, pred: np.ndarray) -> float:
     """bach_mpsnr (:48-58) on ``[1,B,h,w]`` tensors."""
     return float(np.mean([psnr_ref(clean[0, k], pred[0, k]) for k in range(clean.shape[1])]))
+
+
+# --------------------------------------------------------------------------
+# PnP denoiser: NLmeansfilter.m on a K x 1 column  (pnp_ista.m:30, NLmeansfilter.m:1-91)
+# PARITY UNPINNED: no MATLAB/Octave here and the Python scripts call skimage's denoise_nl_means instead
+# (absent, version unpinned).  This restates the in-repo MATLAB file; nothing executes the original.
+# --------------------------------------------------------------------------
+def nlm_kernel_rowsums(f: int = 3) -> np.ndarray:
+    """Row sums of make_kernel(f)/sum (NLmeansfilter.m:80-91,27).  On a single-column input the symmetric padding
+    (:24) makes all 2f+1 window columns identical, so the 2-D weighted distance (:63) collapses to these taps."""
+    k = np.zeros((2 * f + 1, 2 * f + 1))
+    for d in range(1, f + 1):
+        k[f - d:f + d + 1, f - d:f + d + 1] += 1.0 / (2 * d + 1) ** 2
+    k /= f
+    k /= k.sum()
+    return k.sum(axis=1)
+
+
+def nlm_column(x: np.ndarray, t: int, f: int, h: float) -> np.ndarray:
+    """NLmeansfilter(x, t, f, h) for x of shape (K,) or (K,1): search radius t along the column only (the search
+    window is clipped to the real column, :46-49), patch radius f, weights exp(-d/h^2) (:29,65), centre pixel
+    weighted by the maximum weight (:77-78), input returned where the weights underflow to zero (:80-84)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    K = x.shape[0]
+    xp = np.pad(x, f, mode="symmetric")
+    kw = nlm_kernel_rowsums(f)
+    h2 = float(h) * float(h)
+    out = np.empty(K)
+    for i in range(K):
+        w1 = xp[i:i + 2 * f + 1]
+        wmax = avg = sw = 0.0
+        for r in range(max(i - t, 0), min(i + t, K - 1) + 1):
+            if r == i:
+                continue
+            w2 = xp[r:r + 2 * f + 1]
+            d = float(np.sum(kw * (w1 - w2) ** 2))
+            w = math.exp(-d / h2) if h2 > 0 else (1.0 if d == 0 else 0.0)
+            wmax = max(wmax, w)
+            sw += w
+            avg += w * x[r]
+        avg += wmax * x[i]
+        sw += wmax
+        out[i] = avg / sw if sw > 0 else x[i]
+    return out
+
+
+def pnp_ista_nlm(y: np.ndarray, H: np.ndarray, lambda_ista: float, Nit: int, a: float, h_scale: float = 0.1,
+                 t: int = 3, f: int = 3) -> np.ndarray:
+    """pnp_ista.m:14-32: x0 = 0; T = lambda/(2 a); x <- NLmeansfilter(x + H'(y - Hx)/a, 3, 3, 0.1 T)."""
+    H = np.asarray(H, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    x = np.zeros((H.shape[1], 1))
+    T = lambda_ista / (2 * a)
+    for _ in range(Nit):
+        g = x + (H.T @ (y - H @ x)) / a
+        x = nlm_column(g, t, f, h_scale * T).reshape(-1, 1)
+    return x

@@ -188,3 +188,18 @@ def test_input_mpsnr_kat(golden):
     noisy = matio.fold_cube(gi["base_Y"], 36, 36)
     clean = matio.fold_cube(gi["base_clean"], 36, 36)
     assert abs(orc.mpsnr_ref(clean, noisy) - 33.074) < 1e-3
+
+
+# ---------------------------------------------------------------- NLM restatement (parity unpinned: no MATLAB here)
+def test_nlm_restatement_properties():
+    kw = orc.nlm_kernel_rowsums(3)
+    assert abs(kw.sum() - 1) < 1e-12 and np.allclose(kw, kw[::-1])
+    assert np.allclose(kw, [1 / 21, 4 / 35, 71 / 315, 71 / 315, 71 / 315, 4 / 35, 1 / 21])
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(40)
+    # h -> 0: every weight underflows and the filter returns its input (NLmeansfilter.m:80-84)
+    assert np.array_equal(orc.nlm_column(x, 3, 3, 1e-6), x)
+    # constant signal is a fixed point; huge h = plain average over the +-3 search window
+    assert np.allclose(orc.nlm_column(np.full(20, 2.5), 3, 3, 0.1), 2.5)
+    big = orc.nlm_column(x, 3, 3, 1e6)
+    assert abs(big[10] - x[7:14].mean()) < 1e-6
