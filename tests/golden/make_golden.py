@@ -17,6 +17,7 @@ Outputs (all small, committed):
   prox_kat.npz         SVT / Shrinkage_Operator / soft_thresh / l1_prox
   bundled_inputs.npz   unfolded Y_observed / clean / pixel masks of two bundled cubes
   e2e_bundled.npz      2 outer iterations of the literal LRS-PnP loop, base cube, synthetic D (K=324)
+  metrics_kat.npz      bach_mpsnr / pytorch_ssim.ssim / state_convergence of the reference on two bundled cubes
   e2e_small.npz        2 outer iterations, synthetic 12x12x20 cube, bb=8 stride 1, K=128 (spectral and frob4)
 """
 from __future__ import annotations
@@ -227,6 +228,26 @@ def make_e2e_small():
     print("e2e_small done")
 
 
+def make_metrics_kat():
+    """Reference metrics on the bundled cubes: bach_mpsnr (main_LRS_PnP.py:48-58) and pytorch_ssim.ssim
+    (pytorch_ssim/__init__.py:65-73), both imported/extracted from the reference."""
+    sys.path.insert(0, rx.REFERENCE_ROOT)
+    import pytorch_ssim  # the reference's own module
+
+    ns = rx.extract("main_LRS_PnP.py")
+    out = {}
+    for tag, files in dict(base=("low_rank_sparsity_noisy.mat", "low_rank_sparsity_clean.mat"),
+                           img5=("low_rank_sparsity_noisy_img5.mat", "low_rank_sparsity_clean_img5.mat")).items():
+        d = os.path.join(rx.REFERENCE_ROOT, "data")
+        noisy = torch.tensor(matio.load_cube(os.path.join(d, files[0])))
+        clean = torch.tensor(matio.load_cube(os.path.join(d, files[1])))
+        out[f"{tag}_mpsnr_in"] = np.array([ns["bach_mpsnr"](clean, noisy)])
+        out[f"{tag}_mssim_in"] = np.array([float(pytorch_ssim.ssim(clean, noisy))])
+        out[f"{tag}_state"] = np.array([float(ns["state_convergence"](clean, noisy))])
+    np.savez_compressed(os.path.join(HERE, "metrics_kat.npz"), **out)
+    print("metrics_kat:", {k: float(v[0]) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not rx.reference_available():
         sys.exit("reference checkout not found; fixtures can only be generated in the build container")
@@ -236,6 +257,7 @@ if __name__ == "__main__":
     make_bundled_inputs()
     make_e2e_small()
     make_e2e_bundled()
+    make_metrics_kat()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
