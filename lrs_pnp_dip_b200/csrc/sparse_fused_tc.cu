@@ -76,7 +76,8 @@ struct __align__(8) Shared {
     float xmax[4][TILE];      // per-patch partial max |y| of the four pixel quarters
     float xsum[4][TILE];      // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
     uint32_t xrow[TILE];      // validity bits of window column 0 (pixels 0..7)
-    float rn[64];             // ||D[i,:]||^2
+    float rn[64];             // ||Dh[i,:]||^2 (normalised dictionary)
+    uint32_t dmax_bits;       // max |D| as float bits
 };
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NEPI) : "memory"); }
@@ -123,9 +124,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     const int Nit = prm.Nit;
 
     // ---- one-time setup: D -> fp16 pieces, barriers, TMEM -------------------------------------------
+    // The dictionary is normalised by an exact power of two, Dh = sd * D with max |Dh| in [0.5, 1), so that its
+    // fp16 pieces are well scaled whatever the scale of D.  In "hat" units alpha_h = alpha'/sd, a_h = a sd^2:
+    //     at_h <- soft(at_h + r Dh, lambda' sd / 2),   D alpha' = (Dh at_h) / a_h      (at_h = a_h alpha_h)
+    if (tid == 0) sh.dmax_bits = 0u;
+    __syncthreads();
+    {
+        float mx = 0.f;
+        for (int e = tid; e < 64 * KATOMS; e += NTHREADS) mx = fmaxf(mx, fabsf(prm.D[e]));
+        atomicMax(&sh.dmax_bits, __float_as_uint(mx));   // non-negative floats order like their bit patterns
+    }
+    __syncthreads();
+    int dex = 0;
+    {
+        const float dmax = __uint_as_float(sh.dmax_bits);
+        if (dmax > 0.f && dmax < INFINITY) (void)frexpf(dmax, &dex);
+    }
+    const float sd = ldexpf(1.0f, -dex);
     for (int e = tid; e < 64 * KATOMS; e += NTHREADS) {
         int i = e / KATOMS, k = e % KATOMS;
-        float v = prm.D[e] * S_D;
+        float v = prm.D[e] * (sd * S_D);
         __half h1 = __float2half_rn(v);
         __half h2 = __float2half_rn(v - __half2float(h1));
         uint32_t off = (uint32_t)((k % 8) * 2 + (i % 8) * 16) + (uint32_t)(i / 8) * D_SI + (uint32_t)(k / 8) * D_SK;
@@ -135,10 +153,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     if (tid < 64) {
         float s = 0.f;
         for (int k = 0; k < KATOMS; ++k) {
-            float d = prm.D[tid * KATOMS + k];
+            float d = prm.D[tid * KATOMS + k] * sd;
             s = fmaf(d, d, s);
         }
-        sh.rn[tid] = s;
+        sh.rn[tid] = s;                                  // ||Dh[i,:]||^2
     }
     if (tid == 0) {
         mbar_init(&sh.bar_B, 1);
@@ -269,15 +287,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 a += sh.xsum[g2][m];
             }
             a *= 4.0f;                                              // 4 ||H||_F^2 (main_LRS_PnP_DIP_pro.py:190)
-            if (prm.a_patch) a = __ldg(prm.a_patch + p);
-            else if (prm.a_table) a = __ldg(prm.a_table + sh.xrow[m]);
+            if (prm.a_patch) a = __ldg(prm.a_patch + p) * (sd * sd);          // caller's a refers to D: a_h = a sd^2
+            else if (prm.a_table) a = __ldg(prm.a_table + sh.xrow[m]) * (sd * sd);
             epi_barrier();  // exchange buffers are free for the next tile
             const bool ok_a = a > 0.0f;
             const float inv_a = ok_a ? __fdiv_rn(1.0f, a) : 0.0f;
             int ex = 0;
             if (amax > 0.0f) (void)frexpf(amax, &ex);          // amax = f * 2^ex, f in [0.5, 1)
             const float dn = ldexpf(1.0f, -ex), up = ldexpf(1.0f, ex);
-            const float Tn = ok_a ? 0.5f * prm.lambda * dn : 0.0f;  // a * T = lambda / 2 (ista.m:17), normalised
+            const float Tn = ok_a ? 0.5f * prm.lambda * dn * sd : 0.0f;  // a_h * T_h = lambda' sd / 2 (ista.m:17)
             const float c1 = S_R * dn;                            // y -> scaled residual units
             const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= S_ALPHA S_D a D alpha') -> scaled residual units
 #pragma unroll
