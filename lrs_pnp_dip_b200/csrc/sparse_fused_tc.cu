@@ -65,11 +65,18 @@ constexpr float S_R = 0.25f;         // residual pieces = fp16(r / 4)  (S_R * S_
 // D pieces in shared memory, one copy for both GEMMs (bytes):
 //   (k%8)*2 + (i%8)*16 + (8*piece + i/8)*128 + (k/8)*2048       i = pixel (row of D), k = atom
 constexpr uint32_t D_SMEM_BYTES = 64 * 1024;
+// GEMM-B variant: residual pieces as the A operand from SHARED memory (SS form) and the 256 atoms in two N = 128
+// halves, so that the soft-threshold of the first half overlaps the MMAs of the second (an N = 128 MMA with A in
+// shared memory runs at its 64-cycle MAC floor; with A in TMEM it would cost 88).  false = A from TMEM, N = 256.
+constexpr bool B_SS = true;
+// residual pieces in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048 + piece*16384
+constexpr uint32_t R_SMEM_BYTES = B_SS ? 32 * 1024 : 0;
+constexpr uint32_t R_SK = 2048, R_SM = 128, R_PIECE = 16 * 1024;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 
 struct __align__(8) Shared {
     uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in TMEM        (4 warps)
-    uint64_t bar_B;           // MMA -> epilogue: GEMM-B complete, state accumulators final               (commit)
+    uint64_t bar_B[2];        // MMA -> epilogue: GEMM-B complete for atom half h (h = 0 only when !B_SS)      (commit)
     uint64_t bar_S[NCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
     uint64_t bar_A[NCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
     uint32_t tmem_base;
@@ -116,7 +123,8 @@ template <bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
-    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES);
+    uint8_t* Rsm = smem + D_SMEM_BYTES;
+    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = prm.p_end - prm.p_begin;
@@ -159,7 +167,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         sh.rn[tid] = s;                                  // ||Dh[i,:]||^2
     }
     if (tid == 0) {
-        mbar_init(&sh.bar_B, 1);
+        mbar_init(&sh.bar_B[0], 1);
+        mbar_init(&sh.bar_B[1], 1);
         for (int j = 0; j < 4; ++j) mbar_init(&sh.bar_R[j], 4);
         for (int j = 0; j < NCHUNK; ++j) {
             mbar_init(&sh.bar_S[j], NEPI);
@@ -194,27 +203,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
+                if (B_SS) {
+                    const uint32_t idescB128 = make_idesc_f16(128, 128, /*b_mn_major=*/true);
+                    const uint64_t descR0 = make_smem_desc(smem_u32(Rsm), /*lbo=*/R_SK, /*sbo=*/R_SM);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    // quarters become ready in the order the epilogue threads produce them: 0,2,1,3 when a thread
-                    // owns two consecutive quarters
-                    const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;
-                    long long w0 = TSTAMP();
-                    mbar_wait(&sh.bar_R[ks], par);
-                    if (DBG) dbg[1 + kk] += clock64() - w0;
-                    tc_fence_after();
-                    const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI) >> 4);
-                    const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI) >> 4);
-                    const uint32_t r1 = tbase + COL_STG0 + 8 * ks, r2 = tbase + COL_STG0 + 32 + 8 * ks;
-                    if (leader) {
-                        mma_f16_ts(tbase + COL_ALPHA, r1, d1, idescB, !(it == 0 && kk == 0));
-                        mma_f16_ts(tbase + COL_ALPHA, r2, d1, idescB, true);
-                        mma_f16_ts(tbase + COL_ALPHA, r1, d2, idescB, true);
+                    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;   // 0,2,1,3: order of readiness
+                            if (half == 0) {
+                                long long w0 = TSTAMP();
+                                mbar_wait(&sh.bar_R[ks], par);
+                                if (DBG) dbg[1 + kk] += clock64() - w0;
+                                tc_fence_after();
+                            }
+                            const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * 16 * D_SK) >> 4);
+                            const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI + half * 16 * D_SK) >> 4);
+                            const uint64_t r1 = descR0 + (uint64_t)((2 * ks * R_SK) >> 4);
+                            const uint64_t r2 = descR0 + (uint64_t)((R_PIECE + 2 * ks * R_SK) >> 4);
+                            const uint32_t acc = tbase + COL_ALPHA + 128 * half;
+                            if (leader) {
+                                mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && kk == 0));
+                                mma_f16_ss(acc, r2, d1, idescB128, true);
+                                mma_f16_ss(acc, r1, d2, idescB128, true);
+                            }
+                            __syncwarp();
+                        }
+                        if (leader) mma_commit(&sh.bar_B[half]);
+                        __syncwarp();
                     }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // quarters become ready in the order the epilogue threads produce them: 0,2,1,3 when a thread
+                        // owns two consecutive quarters
+                        const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;
+                        long long w0 = TSTAMP();
+                        mbar_wait(&sh.bar_R[ks], par);
+                        if (DBG) dbg[1 + kk] += clock64() - w0;
+                        tc_fence_after();
+                        const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI) >> 4);
+                        const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI) >> 4);
+                        const uint32_t r1 = tbase + COL_STG0 + 8 * ks, r2 = tbase + COL_STG0 + 32 + 8 * ks;
+                        if (leader) {
+                            mma_f16_ts(tbase + COL_ALPHA, r1, d1, idescB, !(it == 0 && kk == 0));
+                            mma_f16_ts(tbase + COL_ALPHA, r2, d1, idescB, true);
+                            mma_f16_ts(tbase + COL_ALPHA, r1, d2, idescB, true);
+                        }
+                        __syncwarp();
+                    }
+                    if (leader) mma_commit(&sh.bar_B[0]);
                     __syncwarp();
                 }
-                if (leader) mma_commit(&sh.bar_B);
-                __syncwarp();
                 // ---- GEMM-A: Da = state D^T, chunk by chunk as the soft-threshold epilogue releases them ----
 #pragma unroll
                 for (int j = 0; j < NCHUNK; ++j) {
@@ -339,9 +379,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                             split_pair(r0, r1, p1[c], p2[c]);
                         }
                     }
-                    tmem_st8(lane_addr + COL_STG0 + 8 * ks, p1);
-                    tmem_st8(lane_addr + COL_STG0 + 32 + 8 * ks, p2);
-                    tmem_wait_st();
+                    if (B_SS) {
+                        // 16 pixels = k-groups 2ks, 2ks+1 of my row m: two 16-byte stores per piece (a warp covers 512
+                        // contiguous bytes per store: conflict-free), then publish to the async proxy
+                        uint8_t* rrow = Rsm + (uint32_t)(m >> 3) * R_SM + (uint32_t)(m & 7) * 16 + (uint32_t)(2 * ks) * R_SK;
+                        *reinterpret_cast<uint4*>(rrow) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                        *reinterpret_cast<uint4*>(rrow + R_SK) = make_uint4(p1[4], p1[5], p1[6], p1[7]);
+                        *reinterpret_cast<uint4*>(rrow + R_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        *reinterpret_cast<uint4*>(rrow + R_PIECE + R_SK) = make_uint4(p2[4], p2[5], p2[6], p2[7]);
+                        fence_async_smem();
+                    } else {
+                        tmem_st8(lane_addr + COL_STG0 + 8 * ks, p1);
+                        tmem_st8(lane_addr + COL_STG0 + 32 + 8 * ks, p2);
+                        tmem_wait_st();
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.bar_R[ks]);
@@ -350,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 //      flight while chunk j is processed. ----
                 const long long ts0 = TSTAMP();
                 if (DBG) ed[5] += ts0 - tr0;
-                mbar_wait(&sh.bar_B, par);
+                mbar_wait(&sh.bar_B[0], par);
                 if (DBG) ed[2] += clock64() - ts0;
                 tc_fence_after();
                 uint32_t ga[CW], gb[CW];
@@ -361,8 +412,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     uint32_t* gn = (j & 1) ? ga : gb;
                     uint32_t p1[CW / 2], p2[CW / 2];
                     const uint32_t col = COL_ALPHA + 64 * j + CW * cg;
+                    if (B_SS && j == 2) {  // atoms 128..255 belong to the second GEMM-B half: no prefetch across it
+                        mbar_wait(&sh.bar_B[1], par);
+                        tc_fence_after();
+                        tmem_ldN<CW>(lane_addr + col, g);
+                    }
                     tmem_wait_ld();
-                    if (j + 1 < NCHUNK) tmem_ldN<CW>(lane_addr + col + 64, gn);
+                    if (j + 1 < NCHUNK && !(B_SS && j + 1 == 2)) tmem_ldN<CW>(lane_addr + col + 64, gn);
 #pragma unroll
                     for (int c = 0; c < CW / 2; ++c) {
                         float x0 = soft_thr(__uint_as_float(g[2 * c]), Tn);
@@ -431,7 +487,7 @@ bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
 int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     if (!sparse_fused_tc_supported(prm, K)) return fail_arg(fn, "tcgen05 engine needs K = 256, Nit >= 1 and an sm_100 device");
-    const size_t smem = D_SMEM_BYTES + sizeof(Shared);
+    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + sizeof(Shared);
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
     auto kern = dbg ? sparse_fused_tc_kernel<true> : sparse_fused_tc_kernel<false>;
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
