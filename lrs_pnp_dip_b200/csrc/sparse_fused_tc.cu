@@ -72,6 +72,14 @@ constexpr bool B_SS = true;
 // residual pieces in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048 + piece*16384
 constexpr uint32_t R_SMEM_BYTES = B_SS ? 32 * 1024 : 0;
 constexpr uint32_t R_SK = 2048, R_SM = 128, R_PIECE = 16 * 1024;
+// GEMM-A variant: the second state piece (a2) as the A operand from SHARED memory (an N = 64 MMA costs 60 cycles with A in
+// shared memory, 88 with A in TMEM).  With a2 out of TMEM the four a1 chunks (32 columns each) fit the 128 staging
+// columns side by side, so the staging double-buffer hazard (and its barrier waits) disappears.  Requires B_SS.
+constexpr bool A2_SS = false;   // measured on B200: 690 ms vs 655 ms (cfg 4) — the extra shared-memory reads contend with B's
+static_assert(!A2_SS || B_SS, "A2_SS uses staging buffer 0 for a1 chunks: the residual pieces must live in shared memory");
+// a2 in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048     (k = atom 0..255)
+constexpr uint32_t A2_SMEM_BYTES = A2_SS ? 64 * 1024 : 0;
+constexpr uint32_t A2_SK = 2048, A2_SM = 128;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 
 struct __align__(8) Shared {
@@ -124,7 +132,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
     uint8_t* Rsm = smem + D_SMEM_BYTES;
-    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES);
+    uint8_t* A2sm = smem + D_SMEM_BYTES + R_SMEM_BYTES;
+    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = prm.p_end - prm.p_begin;
@@ -262,16 +271,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     mbar_wait(&sh.bar_S[j], par);
                     if (DBG) dbg[5 + j] += clock64() - w1;
                     tc_fence_after();
-                    const uint32_t stg = tbase + ((j & 1) ? COL_STG1 : COL_STG0);
+                    const uint32_t stg = tbase + (A2_SS ? COL_STG0 + 32 * j : ((j & 1) ? COL_STG1 : COL_STG0));
+                    const uint64_t descA2 = make_smem_desc(smem_u32(A2sm), /*lbo=*/A2_SK, /*sbo=*/A2_SM);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t d = descA0 + (uint64_t)(((8 * j + 2 * ks) * D_SK) >> 4);
+                        const uint64_t a2 = descA2 + (uint64_t)(((8 * j + 2 * ks) * A2_SK) >> 4);
                         if (leader) {
                             mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));  // a1 [D1;D2]
-                            mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);               // a2 D1
+                            if (A2_SS) mma_f16_ss(tbase + COL_ACC, a2, d, idescA64, true);                   // a2 D1 (A from smem)
+                            else mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);          // a2 D1
                         }
                     }
-                    if (j != NCHUNK - 2 && leader) mma_commit(&sh.bar_A[j]);   // nobody waits for chunk NCHUNK-2
+                    // staging-release commits are only needed when chunks share staging buffers; the last chunk always
+                    // signals "Da complete"
+                    if ((j == NCHUNK - 1 || (!A2_SS && j != NCHUNK - 2)) && leader) mma_commit(&sh.bar_A[j]);
                     __syncwarp();
                 }
                 if (DBG) dbg[10] += 1;
@@ -427,16 +441,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                         g[2 * c + 1] = __float_as_uint(x1);
                         split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
                     }
-                    if (j >= 2) {  // staging buffer (j&1) is free once GEMM-A of chunk j-2 has completed
+                    if (!A2_SS && j >= 2) {  // staging buffer (j&1) is free once GEMM-A of chunk j-2 has completed
                         const long long tw = TSTAMP();
                         mbar_wait(&sh.bar_A[j - 2], par);
                         if (DBG) ed[3 + (j - 2)] += clock64() - tw;
                         tc_fence_after();
                     }
-                    const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
                     tmem_stN<CW>(lane_addr + col, g);
-                    tmem_stN<CW / 2>(lane_addr + stg + (CW / 2) * cg, p1);
-                    tmem_stN<CW / 2>(lane_addr + stg + 32 + (CW / 2) * cg, p2);
+                    if (A2_SS) {
+                        tmem_stN<CW / 2>(lane_addr + COL_STG0 + 32 * j + (CW / 2) * cg, p1);
+                        // my CW atoms = CW/8 k-groups of row m: one 16-byte store each (conflict-free: a warp covers 512
+                        // contiguous bytes), then publish to the async proxy
+                        uint8_t* arow = A2sm + (uint32_t)(m >> 3) * A2_SM + (uint32_t)(m & 7) * 16 +
+                                        (uint32_t)(8 * j + (CW / 8) * cg) * A2_SK;
+#pragma unroll
+                        for (int gk = 0; gk < CW / 8; ++gk)
+                            *reinterpret_cast<uint4*>(arow + gk * A2_SK) = make_uint4(p2[4 * gk], p2[4 * gk + 1], p2[4 * gk + 2], p2[4 * gk + 3]);
+                        fence_async_smem();
+                    } else {
+                        const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
+                        tmem_stN<CW / 2>(lane_addr + stg + (CW / 2) * cg, p1);
+                        tmem_stN<CW / 2>(lane_addr + stg + 32 + (CW / 2) * cg, p2);
+                    }
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -487,7 +513,7 @@ bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
 int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     if (!sparse_fused_tc_supported(prm, K)) return fail_arg(fn, "tcgen05 engine needs K = 256, Nit >= 1 and an sm_100 device");
-    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + sizeof(Shared);
+    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + sizeof(Shared);
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
     auto kern = dbg ? sparse_fused_tc_kernel<true> : sparse_fused_tc_kernel<false>;
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
