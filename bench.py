@@ -94,7 +94,7 @@ def run_reference(args, rank):
     vals = []
     sample = ""
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_patch_iters_per_s(Y, pm, D, budget_s=max(2.0, 60.0 / (args.warmup + args.steps)))
+        v, cores, sample = cpu_patch_iters_per_s(Y, pm, D, budget_s=max(1.0, args.ref_seconds / max(1, args.warmup + args.steps)))
         if i >= args.warmup:
             vals.append(v)
     val = float(np.mean(vals))
@@ -357,6 +357,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="total CPU budget of the --impl reference run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
