@@ -19,6 +19,7 @@ names); other strides run unsharded.
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 from typing import Callable, Optional, Tuple
 
@@ -29,6 +30,13 @@ from . import _lib, ops
 from ._lib import check, lib, ptr, stream_ptr
 
 FUSED_K = (64, 128, 192, 256)
+
+
+def _on(t):
+    """The C library launches on the CURRENT CUDA device and stream: make the tensor's device current."""
+    if isinstance(t, torch.Tensor) and t.device.type == "cuda":
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
 
 
 @dataclass
@@ -99,6 +107,10 @@ class SparseCoder:
     which the reference recomputes for every patch in every outer iteration (:134)."""
 
     def __init__(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str = "auto"):
+        with _on(Y_observed):
+            self._init(Y_observed, D, prm, engine)
+
+    def _init(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str):
         _lib.require_cuda()
         if Y_observed.device.type != "cuda" or D.device.type != "cuda":
             raise _lib.LrsError("SparseCoder needs CUDA tensors")
@@ -128,6 +140,10 @@ class SparseCoder:
 
     def phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         """Phi_z [n, P] of main_LRS_PnP.py:259-303 for V = X + lambda_1/mu_1."""
+        with _on(X):
+            return self._phi_z(X, lambda_1)
+
+    def _phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         prm = self.prm
         if self.fused:
             phi = torch.empty((self.n, self.P), dtype=torch.float32, device=X.device)
@@ -143,7 +159,8 @@ class SparseCoder:
 
     def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339)."""
-        return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, self.prm.bb, self.prm.slidingDis)
+        with _on(X):
+            return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, self.prm.bb, self.prm.slidingDis)
 
 
 def sparse_step(X, lambda_1, mu_1, Y_observed, D, bb, slidingDis, lambda_ista, Nit, step="spectral", engine="auto",
@@ -304,6 +321,10 @@ class LRSPnP:
         return self.stripe.rows_owned if self.stripe.world > 1 else self.Y.shape[0]
 
     def step(self) -> None:
+        with _on(self.X):
+            self._step()
+
+    def _step(self) -> None:
         prm, st, be = self.prm, self.stripe, self.be
         own = self.rows_owned
         row_off = st.a if st.world > 1 else 0
