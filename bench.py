@@ -47,6 +47,15 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sust=1400.0, src="fallback")
 
 
+def ncu_traffic(workload, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload (or None)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p)).get(workload, {}).get(str(world))
+    except (OSError, ValueError):
+        return None
+
+
 def make_inputs(workload):
     from lrs_pnp_dip_b200 import synth
 
@@ -332,7 +341,9 @@ def run_ours(args, rank, world, local_rank):
                                                    "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "fused sparse step", "kernel_ms": float(kms.item()),
+                         "traffic": ncu_traffic(args.workload, world), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                         "algorithmic_bytes": 3.0 * 4 * R * C / world + 4.0 * 64 * P_local,
+                         "kernel": "fused sparse step", "kernel_ms": float(kms.item()),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained {pk['bf16_sust']:.0f} ({pk['src']}) / 3 "
                                         "(3 fp16 MMAs per fp32 product; split products not counted as useful flops)",
                          "tf32x3_peak": tf32 / 3.0, "frac_of_tf32x3": achieved / (tf32 / 3.0),
