@@ -41,7 +41,6 @@ using namespace tc;
 
 namespace {
 
-constexpr int KATOMS = 256;
 constexpr int TILE = 128;
 constexpr int NEPI = 8;                        // epilogue warps (8 measured faster than 16: the epilogue is issue-bound)
 constexpr int NCG = NEPI / 4;                  // column groups per TMEM lane quarter
@@ -49,7 +48,7 @@ constexpr int CW = 64 / NCG;                   // columns (of a 64-column chunk)
 constexpr int QPT = CW / 16;                   // 16-pixel residual quarters per epilogue thread
 constexpr int FIRST_EPI = (NEPI == 8) ? 4 : 2; // first epilogue warp (keeps warp % 4 == TMEM lane quarter)
 constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
-constexpr int NCHUNK = 4;                      // soft-threshold / GEMM-A pipeline: 4 chunks of 64 atoms
+constexpr int MAXCHUNK = 4;                    // soft-threshold / GEMM-A pipeline: K/64 chunks of 64 atoms, K <= 256
 constexpr uint32_t COL_ALPHA = 0;    // [0,256)   fp32 state / GEMM-B accumulator
 constexpr uint32_t COL_ACC = 256;    // [256,320) a1 D1 + a2 D1 ; [320,384) a1 D2
 constexpr uint32_t COL_STG0 = 384;   // staging buffers: piece 1 in [+0,+32), piece 2 in [+32,+64)
@@ -85,8 +84,8 @@ constexpr uint32_t D_SK = 2048, D_SI = 128;
 struct __align__(8) Shared {
     uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in TMEM        (4 warps)
     uint64_t bar_B[2];        // MMA -> epilogue: GEMM-B complete for atom half h (h = 0 only when !B_SS)      (commit)
-    uint64_t bar_S[NCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
-    uint64_t bar_A[NCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
+    uint64_t bar_S[MAXCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
+    uint64_t bar_A[MAXCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
     uint32_t tmem_base;
     float xmax[4][TILE];      // per-patch partial max |y| of the four pixel quarters
     float xsum[4][TILE];      // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
@@ -127,8 +126,13 @@ __device__ unsigned long long g_tc_timing[32];
 
 #define TSTAMP() (DBG ? clock64() : 0ll)
 
-template <bool DBG>
+// KATOMS in {128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
+template <bool DBG, int KATOMS>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm) {
+    constexpr int NCHUNK = KATOMS / 64;
+    constexpr int KH = KATOMS / 2;                    // atoms per GEMM-B half (MMA N)
+    constexpr int FIRST_B1_CHUNK = (KH + 63) / 64 - ((KH % 64) ? 1 : 0);   // first chunk touching the second half
+    static_assert(KATOMS % 64 == 0 && KATOMS >= 128 && KATOMS <= 256 && KH % 16 == 0, "unsupported K");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
     uint8_t* Rsm = smem + D_SMEM_BYTES;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         // ================================ MMA issuer ================================
         const uint32_t leader = elect_one();
         const uint32_t dbase = smem_u32(Dsm);
-        const uint32_t idescB = make_idesc_f16(128, 256, /*b_mn_major=*/true);
+        const uint32_t idescB = make_idesc_f16(128, KATOMS, /*b_mn_major=*/true);
         const uint32_t idescA128 = make_idesc_f16(128, 128, false);
         const uint32_t idescA64 = make_idesc_f16(128, 64, false);
         // GEMM-B: B = D as (N = atoms, K = pixels), MN-major: 16-byte atom chunks SBO = D_SK apart, 8-pixel groups
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
                 if (B_SS) {
-                    const uint32_t idescB128 = make_idesc_f16(128, 128, /*b_mn_major=*/true);
+                    const uint32_t idescB128 = make_idesc_f16(128, KH, /*b_mn_major=*/true);
                     const uint64_t descR0 = make_smem_desc(smem_u32(Rsm), /*lbo=*/R_SK, /*sbo=*/R_SM);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -226,11 +230,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                                 if (DBG) dbg[1 + kk] += clock64() - w0;
                                 tc_fence_after();
                             }
-                            const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * 16 * D_SK) >> 4);
-                            const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI + half * 16 * D_SK) >> 4);
+                            const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
+                            const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
                             const uint64_t r1 = descR0 + (uint64_t)((2 * ks * R_SK) >> 4);
                             const uint64_t r2 = descR0 + (uint64_t)((R_PIECE + 2 * ks * R_SK) >> 4);
-                            const uint32_t acc = tbase + COL_ALPHA + 128 * half;
+                            const uint32_t acc = tbase + COL_ALPHA + KH * half;
                             if (leader) {
                                 mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && kk == 0));
                                 mma_f16_ss(acc, r2, d1, idescB128, true);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     }
                     // staging-release commits are only needed when chunks share staging buffers; the last chunk always
                     // signals "Da complete"
-                    if ((j == NCHUNK - 1 || (!A2_SS && j != NCHUNK - 2)) && leader) mma_commit(&sh.bar_A[j]);
+                    if ((j == NCHUNK - 1 || (!A2_SS && j + 2 < NCHUNK)) && leader) mma_commit(&sh.bar_A[j]);
                     __syncwarp();
                 }
                 if (DBG) dbg[10] += 1;
@@ -426,13 +430,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     uint32_t* gn = (j & 1) ? ga : gb;
                     uint32_t p1[CW / 2], p2[CW / 2];
                     const uint32_t col = COL_ALPHA + 64 * j + CW * cg;
-                    if (B_SS && j == 2) {  // atoms 128..255 belong to the second GEMM-B half: no prefetch across it
+                    if (B_SS && j == FIRST_B1_CHUNK) {  // first chunk with atoms of the second GEMM-B half: no prefetch across it
                         mbar_wait(&sh.bar_B[1], par);
                         tc_fence_after();
                         tmem_ldN<CW>(lane_addr + col, g);
                     }
                     tmem_wait_ld();
-                    if (j + 1 < NCHUNK && !(B_SS && j + 1 == 2)) tmem_ldN<CW>(lane_addr + col + 64, gn);
+                    if (j + 1 < NCHUNK && !(B_SS && j + 1 == FIRST_B1_CHUNK)) tmem_ldN<CW>(lane_addr + col + 64, gn);
 #pragma unroll
                     for (int c = 0; c < CW / 2; ++c) {
                         float x0 = soft_thr(__uint_as_float(g[2 * c]), Tn);
@@ -503,19 +507,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 }  // namespace
 
 bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
-    if (K != KATOMS || prm.g.bb != 8 || prm.Nit < 1) return false;
+    if ((K != 128 && K != 192 && K != 256) || prm.g.bb != 8 || prm.Nit < 1) return false;
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
     return major == 10;
 }
 
-int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
+template <int K>
+static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
-    if (!sparse_fused_tc_supported(prm, K)) return fail_arg(fn, "tcgen05 engine needs K = 256, Nit >= 1 and an sm_100 device");
     const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + sizeof(Shared);
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
-    auto kern = dbg ? sparse_fused_tc_kernel<true> : sparse_fused_tc_kernel<false>;
+    auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
     int sms = device_sm_count();
@@ -525,6 +529,16 @@ int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     kern<<<grid, NTHREADS, smem, st>>>(prm);
     note_launch();
     return check_cuda(fn, cudaGetLastError());
+}
+
+int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
+    if (!sparse_fused_tc_supported(prm, K))
+        return fail_arg("lrs_sparse_step_fused_f32", "tcgen05 engine needs K in {128,192,256}, Nit >= 1 and an sm_100 device");
+    switch (K) {
+        case 128: return launch_tc<128>(prm, st);
+        case 192: return launch_tc<192>(prm, st);
+        default: return launch_tc<256>(prm, st);
+    }
 }
 
 int tc_timing_read(unsigned long long* out32) {
