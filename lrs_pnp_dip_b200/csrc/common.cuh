@@ -47,6 +47,14 @@ struct Axis {
         app = (n > n_reg) && (x >= last);
     }
     __host__ __device__ __forceinline__ int count(int64_t x) const {
+        if (len <= 0x7fffffffLL) {  // 32-bit arithmetic: the elementwise kernels call this per element
+            const int xi = (int)x, t = xi - bb + 1, nr = (int)n_reg;
+            int lo = t <= 0 ? 0 : (t + s - 1) / s, hi = xi / s;
+            if (hi > nr - 1) hi = nr - 1;
+            int c = hi - lo + 1;
+            if (c < 0) c = 0;
+            return c + (((n > n_reg) && (x >= last)) ? 1 : 0);
+        }
         int64_t lo, hi;
         bool app;
         cover(x, lo, hi, app);

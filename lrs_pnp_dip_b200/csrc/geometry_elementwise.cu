@@ -60,14 +60,29 @@ __global__ void im2col_kernel(Geom g, const float* __restrict__ X, const float* 
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int j = blockIdx.y;
     if (p >= g.P) return;
-    int64_t ci = p / g.row.n, ri = p - ci * g.row.n;
-    int64_t rs = g.row.start(ri), cs = g.col.start(ci);
+    int64_t ci, ri;
+    if (g.P <= 0x7fffffffLL) {  // 32-bit division on the common sizes
+        const unsigned nr = (unsigned)g.row.n, pu = (unsigned)p;
+        ci = pu / nr;
+        ri = pu - (unsigned)ci * nr;
+    } else {
+        ci = p / g.row.n;
+        ri = p - ci * g.row.n;
+    }
+    const int64_t rs = g.row.start(ri), cs = g.col.start(ci);
     const int bb = g.bb;
+    const float* src = X + rs * g.C + cs + j;
+    const float* lsrc = L ? L + rs * g.C + cs + j : nullptr;
+    float* dst = blocks + (int64_t)(bb * j) * g.P + p;
     for (int i = 0; i < bb; ++i) {
-        int64_t src = (rs + i) * g.C + cs + j;
-        float v = __ldg(X + src);
-        if (L) v = __fadd_rn(v, __fdiv_rn(__ldg(L + src), mu));
-        blocks[(int64_t)(i + bb * j) * g.P + p] = v;
+        float v = __ldg(src);
+        if (lsrc) {
+            v = __fadd_rn(v, __fdiv_rn(__ldg(lsrc), mu));
+            lsrc += g.C;
+        }
+        *dst = v;
+        src += g.C;
+        dst += g.P;
     }
 }
 
@@ -136,10 +151,10 @@ __global__ void __launch_bounds__(256, 6) col2im_kernel(Geom g, const float* __r
 }
 
 __global__ void weight_kernel(Geom g, float* __restrict__ w) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= g.R * g.C) return;
-    int64_t r = i / g.C, c = i - r * g.C;
-    w[i] = (float)(g.row.count(r) * g.col.count(c));
+    const int64_t r = blockIdx.x;                                        // one unfolded row per block row
+    const int64_t c = blockIdx.y * (int64_t)blockDim.x + threadIdx.x;    // bands along the threads
+    if (c >= g.C) return;
+    w[r * g.C + c] = (float)(g.row.count(r) * g.col.count(c));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,7 +303,10 @@ int lrs_coverage_weight_f32(int64_t R, int64_t C, int bb, int s, float* weight_d
     Geom g;
     if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_coverage_weight_f32", "need 0 < bb <= min(R,C) and s > 0");
     if (!weight_dev) return fail_arg("lrs_coverage_weight_f32", "null pointer");
-    weight_kernel<<<blocks_for(R * C, 256), 256, 0, (cudaStream_t)stream>>>(g, weight_dev);
+    const int threads = C >= 256 ? 256 : (int)((C + 31) / 32 * 32);
+    dim3 grid((unsigned)R, blocks_for(C, threads));
+    if (R > 2147483647LL || grid.y > 65535) return fail_arg("lrs_coverage_weight_f32", "matrix too large");
+    weight_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(g, weight_dev);
     LRS_CHECK_LAUNCH("lrs_coverage_weight_f32");
     return LRS_OK;
 }
