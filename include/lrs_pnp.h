@@ -97,6 +97,14 @@ int lrs_axpy_f32(const float* x_dev, const float* l_dev, float c, float* out_dev
 int lrs_step_frob4_f32(const float* blocks_copy_dev, const float* D_dev, int n, int K, int64_t P, float* a_dev,
                        lrs_stream_t stream);
 
+/* table_dev[2^bb] (bb <= 8): step constant for every validity pattern of a patch's bb pixel rows (bit i = row r+i
+ * observed; band-replicated masks, main_LRS_PnP.py:188-192): LRS_STEP_SPECTRAL ||M D||_2^2 (main_LRS_PnP.py:134) or
+ * LRS_STEP_FROB4 (main_LRS_PnP_DIP_pro.py:190).  Replaces one SVD per patch per outer iteration by one table per
+ * dictionary; feeds a_table_dev of lrs_sparse_step_fused_f32. */
+size_t lrs_spectral_table_workspace_bytes(int bb);
+int lrs_spectral_table_f32(const float* D_dev, int K, int bb, int step, float* table_dev, void* workspace_dev,
+                           size_t workspace_bytes, lrs_stream_t stream);
+
 /* ---- batched soft-ISTA on explicit patch matrices ------------------------------------------- */
 /* For every patch p: alpha=0; repeat Nit: alpha <- soft(alpha + D^T(m.*(y - D alpha))/a_p, lambda/(2 a_p))
  * with m = (blocks_copy[:,p] != 0)  [row deletion of main_LRS_PnP.py:276-289 in masked form],

@@ -198,16 +198,17 @@ _TABLE_CACHE: dict = {}
 
 def _row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
     n, K = D.shape
-    i_of_k = torch.arange(n, device=D.device) % bb
-    bits = torch.arange(1 << bb, device=D.device)
-    m = ((bits[:, None] >> i_of_k[None, :]) & 1).to(torch.float64)          # [2^bb, n]
-    Dd = D.to(torch.float64)
-    if step == "frob4":
-        rn = (Dd * Dd).sum(1)
-        return (4.0 * (m @ rn)).to(torch.float32).contiguous()
-    G = Dd @ Dd.T                                                            # [n, n]
-    Gm = m[:, :, None] * G[None] * m[:, None, :]
-    return torch.linalg.eigvalsh(Gm)[:, -1].clamp_min(0).to(torch.float32).contiguous()
+    L = lib()
+    ws_bytes = L.lrs_spectral_table_workspace_bytes(bb)
+    if ws_bytes == 0:
+        raise _lib.LrsError(f"row-pattern step-constant tables exist for bb <= 8 (got bb = {bb})")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=D.device)
+    table = torch.empty(1 << bb, dtype=torch.float32, device=D.device)
+    mode = {"spectral": _lib.STEP_SPECTRAL, "frob4": _lib.STEP_FROB4}[step]
+    with torch.cuda.device(D.device):
+        check(L.lrs_spectral_table_f32(ptr(D.contiguous()), K, bb, mode, ptr(table), ptr(ws), ws_bytes, stream_ptr()),
+              "lrs_spectral_table_f32")
+    return table
 
 
 # ------------------------------------------------------------------ ista
