@@ -123,6 +123,96 @@ __global__ void __launch_bounds__(256) sgemm_kernel(ALoad aload, const float* __
     }
 }
 
+// Software-pipelined variant for the ISTA GEMMs (plain pointer A operand): 48-column tiles (P = 144 = 3 x 48 on the
+// bundled configs, no padded columns), BMv = 32 or 64 rows so that the tall-skinny problems fill the SMs, double-buffered
+// shared memory with the next k-tile prefetched into registers while the current one is multiplied.
+template <bool TRANS_A, class Epi, int BMv>
+__global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t M,
+                                                         int64_t N, int64_t Kd, Epi epi) {
+    constexpr int BNv = 48, TMv = BMv / 16, NT = 192;
+    constexpr int NA = (BK * BMv + NT - 1) / NT, NB = BK * BNv / NT;
+    __shared__ __align__(16) float As[2][BK][BMv + 4];
+    __shared__ __align__(16) float Bs[2][BK][BNv + 4];
+    const int tid = threadIdx.x, tx = tid % 12, ty = tid / 12;
+    const int64_t m0 = blockIdx.y * (int64_t)BMv, n0 = blockIdx.x * (int64_t)BNv;
+    float acc[TMv][4];
+#pragma unroll
+    for (int i = 0; i < TMv; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float ra[NA], rb[NB];
+
+    auto gload = [&](int64_t k0) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            const int e = tid + u * NT;
+            float v = 0.f;
+            if (e < BK * BMv) {
+                const int k = TRANS_A ? e / BMv : e % BK, m = TRANS_A ? e % BMv : e / BK;
+                const int64_t gk = k0 + k, gm = m0 + m;
+                if (gk < Kd && gm < M) v = __ldg(A + (TRANS_A ? gk * M + gm : gm * Kd + gk));
+            }
+            ra[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * NT, k = e / BNv, n = e % BNv;
+            const int64_t gk = k0 + k, gn = n0 + n;
+            rb[u] = (gk < Kd && gn < N) ? __ldg(B + gk * N + gn) : 0.f;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            const int e = tid + u * NT;
+            if (e < BK * BMv) {
+                const int k = TRANS_A ? e / BMv : e % BK, m = TRANS_A ? e % BMv : e / BK;
+                As[buf][k][m] = ra[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int e = tid + u * NT;
+            Bs[buf][e / BNv][e % BNv] = rb[u];
+        }
+    };
+
+    const int64_t nk = (Kd + BK - 1) / BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int64_t kt = 0; kt < nk; ++kt) {
+        const int buf = (int)(kt & 1);
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TMv];
+#pragma unroll
+            for (int i = 0; i < TMv; ++i) a[i] = As[buf][k][ty * TMv + i];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TMv; ++i) {
+                acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+            }
+        }
+        if (kt + 1 < nk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TMv; ++i) {
+        const int64_t gm = m0 + ty * TMv + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t gn = n0 + tx * 4 + j;
+            if (gn < N) epi(gm, gn, N, acc[i][j]);
+        }
+    }
+}
+
 __global__ void ista_prepare_kernel(const float* __restrict__ a, float lambda, int64_t P, float* __restrict__ inv_a,
                                     float* __restrict__ T) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -181,6 +271,22 @@ static int launch_gemm(const char* fn, ALoad al, const float* B, int64_t M, int6
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
     if (grid.y > 65535) return fail_arg(fn, "matrix too tall for this engine");
     sgemm_kernel<TRANS_A, ALoad, Epi><<<grid, 256, 0, st>>>(al, B, M, N, Kd, epi);
+    note_launch();
+    return check_cuda(fn, cudaGetLastError());
+}
+
+// ISTA GEMMs: pipelined kernel; 32-row tiles when 64-row tiles would leave SMs idle.
+template <bool TRANS_A, class Epi>
+static int launch_gemm(const char* fn, LoadPlain al, const float* B, int64_t M, int64_t N, int64_t Kd, Epi epi,
+                       cudaStream_t st) {
+    static int sms = device_sm_count();
+    const int64_t ncol = (N + 47) / 48;
+    const bool small = ((M + 63) / 64) * ncol < 2 * (int64_t)(sms > 0 ? sms : 148);
+    const int bm = small ? 32 : 64;
+    dim3 grid((unsigned)ncol, (unsigned)((M + bm - 1) / bm));
+    if (grid.y > 65535) return fail_arg(fn, "matrix too tall for this engine");
+    if (small) sgemm_pipe_kernel<TRANS_A, Epi, 32><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, epi);
+    else sgemm_pipe_kernel<TRANS_A, Epi, 64><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, epi);
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
