@@ -12,7 +12,8 @@ namespace lrs {
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 
-struct EpiResidual {  // c = D A  ->  Rm
+struct EpiResidual {
+    __device__ __forceinline__ void slice(int64_t) {}  // c = D A  ->  Rm
     const float* Y;
     const float* BC;
     const float* inv_a;
@@ -23,7 +24,8 @@ struct EpiResidual {  // c = D A  ->  Rm
         out[o] = v;
     }
 };
-struct EpiGradient {  // c = D^T Rm  ->  A = soft(A + c, T)
+struct EpiGradient {
+    __device__ __forceinline__ void slice(int64_t) {}  // c = D^T Rm  ->  A = soft(A + c, T)
     const float* T;
     float* A;
     __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const {
@@ -31,7 +33,8 @@ struct EpiGradient {  // c = D^T Rm  ->  A = soft(A + c, T)
         A[o] = soft_thr(A[o] + acc, T[p]);
     }
 };
-struct EpiGradientPlain {  // c = D^T Rm  ->  G = A + c   (input of a plug-and-play denoiser; identity when G == A buffer)
+struct EpiGradientPlain {
+    __device__ __forceinline__ void slice(int64_t) {}  // c = D^T Rm  ->  G = A + c   (input of a plug-and-play denoiser; identity when G == A buffer)
     const float* A;
     float* G;
     __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const {
@@ -40,8 +43,14 @@ struct EpiGradientPlain {  // c = D^T Rm  ->  G = A + c   (input of a plug-and-p
     }
 };
 struct EpiStore {
+    __device__ __forceinline__ void slice(int64_t) {}
     float* out;
     __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const { out[m * ld + p] = acc; }
+};
+struct EpiPartial {  // split-K: raw partial sums into slice z of a [splits, M, N] buffer
+    float* buf;
+    __device__ __forceinline__ void slice(int64_t off) { buf += off; }
+    __device__ __forceinline__ void operator()(int64_t m, int64_t p, int64_t ld, float acc) const { buf[m * ld + p] = acc; }
 };
 struct LoadPlain {
     const float* B;
@@ -128,7 +137,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(ALoad aload, const float* __
 // shared memory with the next k-tile prefetched into registers while the current one is multiplied.
 template <bool TRANS_A, class Epi, int BMv>
 __global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t M,
-                                                         int64_t N, int64_t Kd, Epi epi) {
+                                                         int64_t N, int64_t Kd, int64_t kchunk, Epi epi_in) {
+    // split-K: block z multiplies k in [z*kchunk, (z+1)*kchunk) and hands its partial sums to slice z of the epilogue
+    const int64_t kbeg = blockIdx.z * kchunk, kend = kbeg + kchunk < Kd ? kbeg + kchunk : Kd;
+    Epi epi = epi_in;
+    epi.slice((int64_t)blockIdx.z * M * N);
     constexpr int BNv = 48, TMv = BMv / 16, NT = 192;
     constexpr int NA = (BK * BMv + NT - 1) / NT, NB = BK * BNv / NT;
     __shared__ __align__(16) float As[2][BK][BMv + 4];
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict
             if (e < BK * BMv) {
                 const int k = TRANS_A ? e / BMv : e % BK, m = TRANS_A ? e % BMv : e / BK;
                 const int64_t gk = k0 + k, gm = m0 + m;
-                if (gk < Kd && gm < M) v = __ldg(A + (TRANS_A ? gk * M + gm : gm * Kd + gk));
+                if (gk < kend && gm < M) v = __ldg(A + (TRANS_A ? gk * M + gm : gm * Kd + gk));
             }
             ra[u] = v;
         }
@@ -158,7 +171,7 @@ __global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict
         for (int u = 0; u < NB; ++u) {
             const int e = tid + u * NT, k = e / BNv, n = e % BNv;
             const int64_t gk = k0 + k, gn = n0 + n;
-            rb[u] = (gk < Kd && gn < N) ? __ldg(B + gk * N + gn) : 0.f;
+            rb[u] = (gk < kend && gn < N) ? __ldg(B + gk * N + gn) : 0.f;
         }
     };
     auto sstore = [&](int buf) {
@@ -177,13 +190,13 @@ __global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict
         }
     };
 
-    const int64_t nk = (Kd + BK - 1) / BK;
-    gload(0);
+    const int64_t nk = (kend - kbeg + BK - 1) / BK;
+    gload(kbeg);
     sstore(0);
     __syncthreads();
     for (int64_t kt = 0; kt < nk; ++kt) {
         const int buf = (int)(kt & 1);
-        if (kt + 1 < nk) gload((kt + 1) * BK);
+        if (kt + 1 < nk) gload(kbeg + (kt + 1) * BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TMv];
@@ -211,6 +224,27 @@ __global__ void __launch_bounds__(192) sgemm_pipe_kernel(const float* __restrict
             if (gn < N) epi(gm, gn, N, acc[i][j]);
         }
     }
+}
+
+// Second pass of a split-K GEMM: add the slices in a fixed order (deterministic), then apply the fused epilogue.
+template <class Epi>
+__global__ void splitk_epilogue_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N, Epi epi) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= M * N) return;
+    float s = partial[e];
+    for (int z = 1; z < splits; ++z) s += partial[(int64_t)z * M * N + e];
+    const int64_t m = e / N;
+    epi(m, e - m * N, N, s);
+}
+
+// Number of k-splits for an ISTA GEMM: enough CTAs for ~4 per SM on the small-P problems, none on the large ones.
+static int ista_splits(int64_t M, int64_t N, int64_t Kd) {
+    const int64_t base = ((M + 31) / 32) * ((N + 47) / 48);
+    int64_t sp = (592 + base - 1) / base;
+    const int64_t by_k = Kd / (8 * BK);      // at least 8 k-tiles per split
+    if (sp > by_k) sp = by_k;
+    if (sp > 8) sp = 8;
+    return sp < 1 ? 1 : (int)sp;
 }
 
 __global__ void ista_prepare_kernel(const float* __restrict__ a, float lambda, int64_t P, float* __restrict__ inv_a,
@@ -275,18 +309,30 @@ static int launch_gemm(const char* fn, ALoad al, const float* B, int64_t M, int6
     return check_cuda(fn, cudaGetLastError());
 }
 
-// ISTA GEMMs: pipelined kernel; 32-row tiles when 64-row tiles would leave SMs idle.
+// ISTA GEMMs: pipelined kernel; 32-row tiles when 64-row tiles would leave SMs idle, and split-K (partials in
+// `scratch`, reduced in a fixed order by splitk_epilogue_kernel) when even those are too few CTAs.
 template <bool TRANS_A, class Epi>
 static int launch_gemm(const char* fn, LoadPlain al, const float* B, int64_t M, int64_t N, int64_t Kd, Epi epi,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* scratch = nullptr) {
     static int sms = device_sm_count();
     const int64_t ncol = (N + 47) / 48;
-    const bool small = ((M + 63) / 64) * ncol < 2 * (int64_t)(sms > 0 ? sms : 148);
+    const int splits = scratch ? ista_splits(M, N, Kd) : 1;
+    const bool small = splits > 1 || ((M + 63) / 64) * ncol < 2 * (int64_t)(sms > 0 ? sms : 148);
     const int bm = small ? 32 : 64;
-    dim3 grid((unsigned)ncol, (unsigned)((M + bm - 1) / bm));
+    dim3 grid((unsigned)ncol, (unsigned)((M + bm - 1) / bm), (unsigned)splits);
     if (grid.y > 65535) return fail_arg(fn, "matrix too tall for this engine");
-    if (small) sgemm_pipe_kernel<TRANS_A, Epi, 32><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, epi);
-    else sgemm_pipe_kernel<TRANS_A, Epi, 64><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, epi);
+    if (splits > 1) {
+        const int64_t kchunk = ((Kd + splits - 1) / splits + BK - 1) / BK * BK;
+        sgemm_pipe_kernel<TRANS_A, EpiPartial, 32><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, kchunk, EpiPartial{scratch});
+        note_launch();
+        int rc = check_cuda(fn, cudaGetLastError());
+        if (rc != LRS_OK) return rc;
+        splitk_epilogue_kernel<Epi><<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(scratch, splits, M, N, epi);
+    } else if (small) {
+        sgemm_pipe_kernel<TRANS_A, Epi, 32><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, Kd, epi);
+    } else {
+        sgemm_pipe_kernel<TRANS_A, Epi, 64><<<grid, 192, 0, st>>>(al.B, B, M, N, Kd, Kd, epi);
+    }
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
@@ -314,9 +360,11 @@ extern "C" {
 
 size_t lrs_ista_workspace_bytes(int n, int K, int64_t P) {
     if (n <= 0 || K <= 0 || P < 0) return 0;
-    // coefs [K,P] + denoiser input [K,P] + residual [n,P] + inv_a [P] + T [P], each 256-byte aligned
+    // coefs [K,P] + denoiser input [K,P] + residual [n,P] + inv_a [P] + T [P] + split-K partials, each 256-byte aligned
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    return 2 * al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4);
+    const size_t s1 = (size_t)lrs::ista_splits(n, P, K) * n, s2 = (size_t)lrs::ista_splits(K, P, n) * K;
+    const size_t part = (s1 > (size_t)n || s2 > (size_t)K) ? al((s1 > s2 ? s1 : s2) * (size_t)P * 4) : 0;
+    return 2 * al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4) + part;
 }
 
 int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
@@ -351,20 +399,22 @@ int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, cons
     float* inv_a = (float*)w;
     w += al((size_t)P * 4);
     float* T = (float*)w;
+    w += al((size_t)P * 4);
+    float* scratch = (ista_splits(n, P, K) > 1 || ista_splits(K, P, n) > 1) ? (float*)w : nullptr;
 
     int rc = check_cuda(fn, cudaMemsetAsync(A, 0, (size_t)K * P * 4, st));  // x0 = 0  (ista.m:14)
     if (rc != LRS_OK) return rc;
     ista_prepare_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a_dev, lambda_ista, P, inv_a, T);
     LRS_CHECK_LAUNCH(fn);
     for (int it = 0; it < Nit; ++it) {
-        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiResidual{blocks_dev, blocks_copy_dev, inv_a, Rm}, st);
+        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiResidual{blocks_dev, blocks_copy_dev, inv_a, Rm}, st, scratch);
         if (rc != LRS_OK) return rc;
         if (denoiser == LRS_DENOISE_SOFT) {
-            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradient{T, A}, st);
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradient{T, A}, st, scratch);
         } else if (denoiser == LRS_DENOISE_IDENTITY) {
-            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, A}, st);
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, A}, st, scratch);
         } else {
-            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, Gd}, st);
+            rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, Gd}, st, scratch);
             if (rc != LRS_OK) return rc;
             dim3 grid((unsigned)((P + 127) / 128), (unsigned)K);
             if (K > 65535) return fail_arg(fn, "K too large for the NLM denoiser");
@@ -375,7 +425,7 @@ int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, cons
         if (rc != LRS_OK) return rc;
     }
     if (phi_z_dev) {
-        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiStore{phi_z_dev}, st);
+        rc = launch_gemm<false>(fn, LoadPlain{D_dev}, A, n, P, K, EpiStore{phi_z_dev}, st, scratch);
         if (rc != LRS_OK) return rc;
     }
     if (coefs_dev) {
