@@ -126,9 +126,48 @@ __device__ unsigned long long g_tc_timing[32];
 
 #define TSTAMP() (DBG ? clock64() : 0ll)
 
+// Tile order.  A tile is TILE consecutive row starts of ONE column start, so its patches read a (TILE+7) x 8 window
+// of the cube.  A CTA walks work items = (row block rb, chunk of column starts): consecutive tiles of an item shift
+// the window by one column, so seven eighths of every gather hit lines the previous tile already pulled into L1/L2
+// and DRAM sees each cube row block about once per item instead of once per tile.  Patch numbering (and the Phi_z
+// column) stays the reference's p = ci * nR + ri (main_LRS_PnP.py:90-99).
+struct TilePlan {
+    int64_t ci0, ci_end;   // column starts touched by [p_begin, p_end)
+    int64_t items;         // rblocks * cchunks
+    int cchunks, cpc;      // chunks per row block, column starts per chunk
+};
+
+struct TileWalk {
+    int64_t item;
+    int rb = 0, ci = 0, c_hi = 0;
+    __device__ TileWalk() : item((int64_t)blockIdx.x - (int64_t)gridDim.x) {}
+    // advance to this CTA's next tile holding at least one patch of [p_begin, p_end); pl and prm are the kernel
+    // parameters (constant bank), so the walker itself only keeps four values live across the iteration loop
+    __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm) {
+        const int64_t nR = prm.g.row.n;
+        for (;;) {
+            if (ci + 1 < c_hi) {
+                ++ci;
+            } else {
+                item += gridDim.x;
+                if (item >= pl.items) return false;
+                rb = (int)(item / pl.cchunks);
+                ci = (int)(pl.ci0 + (item - (int64_t)rb * pl.cchunks) * pl.cpc);
+                c_hi = ci + pl.cpc < (int)pl.ci_end ? ci + pl.cpc : (int)pl.ci_end;
+                if (ci >= c_hi) {
+                    c_hi = ci;
+                    continue;
+                }
+            }
+            const int64_t r0 = (int64_t)rb * TILE, r1 = r0 + TILE < nR ? r0 + TILE : nR;
+            if (ci * nR + r1 > prm.p_begin && ci * nR + r0 < prm.p_end) return true;
+        }
+    }
+};
+
 // KATOMS in {128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
 template <bool DBG, int KATOMS>
-__global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm) {
+__global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm, TilePlan plan) {
     constexpr int NCHUNK = KATOMS / 64;
     constexpr int KH = KATOMS / 2;                    // atoms per GEMM-B half (MMA N)
     constexpr int FIRST_B1_CHUNK = (KH + 63) / 64 - ((KH % 64) ? 1 : 0);   // first chunk touching the second half
@@ -141,7 +180,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = prm.p_end - prm.p_begin;
-    const int64_t ntiles = (total + TILE - 1) / TILE;
     const int Nit = prm.Nit;
 
     // ---- one-time setup: D -> fp16 pieces, barriers, TMEM -------------------------------------------
@@ -212,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0;
         long long dbg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_begin = TSTAMP();
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (TileWalk tw; tw.next(plan, prm);) {
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
@@ -309,13 +347,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0;
         long long ed[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long e_begin = TSTAMP();
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (TileWalk tw; tw.next(plan, prm);) {
             const long long tp0 = TSTAMP();
             // ---- tile prologue: gather my CW pixels (window columns CW/8*cg ..), mask, step constant, scale ----
-            const int64_t pi = tile * TILE + m;
-            const bool valid = pi < total;
-            const int64_t p = prm.p_begin + (valid ? pi : total - 1);
-            const int64_t ci = p / nR, ri = p - ci * nR;
+            int64_t ci = tw.ci, ri = (int64_t)tw.rb * TILE + m;
+            int64_t p = ci * nR + ri;
+            const bool valid = ri < nR && p >= prm.p_begin && p < prm.p_end;
+            const int64_t pi = p - prm.p_begin;                 // Phi_z column
+            if (!valid) {                                       // idle lane: recompute some patch of the range, store nothing
+                p = p < prm.p_begin ? prm.p_begin : prm.p_end - 1;
+                if (ri >= nR && tw.ci * nR + nR - 1 >= prm.p_begin && tw.ci * nR + nR - 1 < prm.p_end) p = tw.ci * nR + nR - 1;
+                ci = p / nR;
+                ri = p - ci * nR;
+            }
             const int64_t rs = prm.g.row.start(ri), cs = prm.g.col.start(ci);
             float ysc[CW];
             uint32_t mbits = 0;
@@ -524,9 +568,20 @@ static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     if (rc != LRS_OK) return rc;
     int sms = device_sm_count();
     if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
-    int64_t ntiles = (prm.p_end - prm.p_begin + TILE - 1) / TILE;
-    unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-    kern<<<grid, NTHREADS, smem, st>>>(prm);
+    // work items: every row block of TILE row starts, cut into enough column-start chunks that the persistent grid
+    // stays balanced (>= ~100 items per SM when the problem has them) while a chunk still reuses its window.
+    const int64_t nR = prm.g.row.n;
+    TilePlan plan;
+    plan.ci0 = prm.p_begin / nR;
+    plan.ci_end = (prm.p_end - 1) / nR + 1;
+    const int64_t ncols = plan.ci_end - plan.ci0, rblocks = (nR + TILE - 1) / TILE;
+    int64_t cchunks = (100 * (int64_t)sms + rblocks - 1) / rblocks;
+    cchunks = cchunks < 1 ? 1 : (cchunks > ncols ? ncols : cchunks);
+    plan.cchunks = (int)cchunks;
+    plan.cpc = (int)((ncols + cchunks - 1) / cchunks);
+    plan.items = rblocks * cchunks;
+    unsigned grid = (unsigned)(plan.items < sms ? plan.items : sms);
+    kern<<<grid, NTHREADS, smem, st>>>(prm, plan);
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
