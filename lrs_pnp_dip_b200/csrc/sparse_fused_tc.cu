@@ -74,10 +74,23 @@ constexpr uint32_t R_SK = 2048, R_SM = 128, R_PIECE = 16 * 1024;
 // GEMM-A variant: the second state piece (a2) as the A operand from SHARED memory (an N = 64 MMA costs 60 cycles with A in
 // shared memory, 88 with A in TMEM).  With a2 out of TMEM the four a1 chunks (32 columns each) fit the 128 staging
 // columns side by side, so the staging double-buffer hazard (and its barrier waits) disappears.  Requires B_SS.
-constexpr bool A2_SS = false;   // measured on B200: 690 ms vs 655 ms (cfg 4) — the extra shared-memory reads contend with B's
+#ifdef LRS_A2_SS
+constexpr bool A2_SS = true;
+#else
+constexpr bool A2_SS = false;
+#endif
+// A2_SS measured on B200: 690 ms vs 655 ms (cfg 4) — the extra shared-memory reads contend with B's
 static_assert(!A2_SS || B_SS, "A2_SS uses staging buffer 0 for a1 chunks: the residual pieces must live in shared memory");
 // a2 in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048     (k = atom 0..255)
-constexpr uint32_t A2_SMEM_BYTES = A2_SS ? 64 * 1024 : 0;
+// experiment: the first state piece from shared memory as well, so that every MMA of the kernel is an SS form
+#ifdef LRS_A1_SS
+constexpr bool A1_SS = true;
+#else
+constexpr bool A1_SS = false;
+#endif
+static_assert(!A1_SS || A2_SS, "A1_SS extends A2_SS");
+constexpr uint32_t A2_SMEM_BYTES = (A2_SS ? 64 * 1024 : 0) + (A1_SS ? 64 * 1024 : 0);
+constexpr uint32_t A1_OFF = 64 * 1024;   // a1 pieces follow the a2 pieces, same layout
 constexpr uint32_t A2_SK = 2048, A2_SM = 128;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 
@@ -87,8 +100,8 @@ struct __align__(8) Shared {
     uint64_t bar_S[MAXCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
     uint64_t bar_A[MAXCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
     uint32_t tmem_base;
-    float xmax[4][TILE];      // per-patch partial max |y| of the four pixel quarters
-    float xsum[4][TILE];      // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
+    float xmax[NCG][TILE];    // per-patch partial max |y| of the pixel groups
+    float xsum[NCG][TILE];    // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
     uint32_t xrow[TILE];      // validity bits of window column 0 (pixels 0..7)
     float rn[64];             // ||Dh[i,:]||^2 (normalised dictionary)
     uint32_t dmax_bits;       // max |D| as float bits
@@ -98,13 +111,46 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 
 __device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
+// Packed fp32 pairs (sm_100 add/sub/fma.f32x2 -> FADD2 / FFMA2): the epilogue is instruction-issue bound and every
+// value it touches comes in pairs, so one instruction per two elements halves its FP32-pipe instruction count.  The
+// results are the same IEEE round-to-nearest values as the scalar forms.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // x (already scaled) -> two fp16 pieces, two values per 32-bit word
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p1, uint32_t& p2) {
     __half2 h = __floats2half2_rn(x0, x1);
     float2 f = __half22float2(h);
-    __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    float l0, l1;
+    upk2(sub2(pk2(x0, x1), pk2(f.x, f.y)), l0, l1);
+    __half2 l = __floats2half2_rn(l0, l1);
     p1 = pack_h2(h);
     p2 = pack_h2(l);
+}
+
+// soft(g, T) = g - clamp(g, -T, T) for a pair (two min/max each, one packed subtract)
+__device__ __forceinline__ void soft_pair(float g0, float g1, float T, float& x0, float& x1) {
+    const float t0 = fminf(fmaxf(g0, -T), T), t1 = fminf(fmaxf(g1, -T), T);
+    upk2(sub2(pk2(g0, g1), pk2(t0, t1)), x0, x1);
 }
 
 template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t a, uint32_t* r) {
@@ -320,7 +366,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                         const uint64_t d = descA0 + (uint64_t)(((8 * j + 2 * ks) * D_SK) >> 4);
                         const uint64_t a2 = descA2 + (uint64_t)(((8 * j + 2 * ks) * A2_SK) >> 4);
                         if (leader) {
-                            mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));  // a1 [D1;D2]
+                            if (A1_SS) mma_f16_ss(tbase + COL_ACC, a2 + (uint64_t)(A1_OFF >> 4), d, idescA128, !(j == 0 && ks == 0));
+                            else mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));  // a1 [D1;D2]
                             if (A2_SS) mma_f16_ss(tbase + COL_ACC, a2, d, idescA64, true);                   // a2 D1 (A from smem)
                             else mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);          // a2 D1
                         }
@@ -402,6 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= S_ALPHA S_D a D alpha') -> scaled residual units
 #pragma unroll
             for (int c = 0; c < CW; ++c) ysc[c] *= c1;
+            const uint64_t nc2 = pk2(-c2, -c2);
             if (DBG) ed[7] += clock64() - tp0;
 
             for (int it = 0; it < Nit; ++it, ++gi) {
@@ -426,10 +474,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const int e = 16 * qq + 2 * c;
-                            float s0 = __uint_as_float(a0[2 * c]) + __uint_as_float(a1[2 * c]);
-                            float s1 = __uint_as_float(a0[2 * c + 1]) + __uint_as_float(a1[2 * c + 1]);
-                            float r0 = ((mbits >> e) & 1u) ? fmaf(-c2, s0, ysc[e]) : 0.f;
-                            float r1 = ((mbits >> (e + 1)) & 1u) ? fmaf(-c2, s1, ysc[e + 1]) : 0.f;
+                            const uint64_t sm2 = add2(pk2(__uint_as_float(a0[2 * c]), __uint_as_float(a0[2 * c + 1])),
+                                                      pk2(__uint_as_float(a1[2 * c]), __uint_as_float(a1[2 * c + 1])));
+                            float r0, r1;
+                            upk2(fma2(nc2, sm2, pk2(ysc[e], ysc[e + 1])), r0, r1);
+                            r0 = ((mbits >> e) & 1u) ? r0 : 0.f;
+                            r1 = ((mbits >> (e + 1)) & 1u) ? r1 : 0.f;
                             split_pair(r0, r1, p1[c], p2[c]);
                         }
                     } else {
@@ -483,8 +533,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     if (j + 1 < NCHUNK && !(B_SS && j + 1 == FIRST_B1_CHUNK)) tmem_ldN<CW>(lane_addr + col + 64, gn);
 #pragma unroll
                     for (int c = 0; c < CW / 2; ++c) {
-                        float x0 = soft_thr(__uint_as_float(g[2 * c]), Tn);
-                        float x1 = soft_thr(__uint_as_float(g[2 * c + 1]), Tn);
+                        float x0, x1;
+                        soft_pair(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), Tn, x0, x1);
                         g[2 * c] = __float_as_uint(x0);
                         g[2 * c + 1] = __float_as_uint(x1);
                         split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
@@ -497,7 +547,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     }
                     tmem_stN<CW>(lane_addr + col, g);
                     if (A2_SS) {
-                        tmem_stN<CW / 2>(lane_addr + COL_STG0 + 32 * j + (CW / 2) * cg, p1);
+                        if (!A1_SS) tmem_stN<CW / 2>(lane_addr + COL_STG0 + 32 * j + (CW / 2) * cg, p1);
                         // my CW atoms = CW/8 k-groups of row m: one 16-byte store each (conflict-free: a warp covers 512
                         // contiguous bytes), then publish to the async proxy
                         uint8_t* arow = A2sm + (uint32_t)(m >> 3) * A2_SM + (uint32_t)(m & 7) * 16 +
@@ -505,6 +555,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 #pragma unroll
                         for (int gk = 0; gk < CW / 8; ++gk)
                             *reinterpret_cast<uint4*>(arow + gk * A2_SK) = make_uint4(p2[4 * gk], p2[4 * gk + 1], p2[4 * gk + 2], p2[4 * gk + 3]);
+                        if (A1_SS) {
+#pragma unroll
+                            for (int gk = 0; gk < CW / 8; ++gk)
+                                *reinterpret_cast<uint4*>(arow + A1_OFF + gk * A2_SK) = make_uint4(p1[4 * gk], p1[4 * gk + 1], p1[4 * gk + 2], p1[4 * gk + 3]);
+                        }
                         fence_async_smem();
                     } else {
                         const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
