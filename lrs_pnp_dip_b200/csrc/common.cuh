@@ -40,16 +40,23 @@ struct Axis {
     // Range of regular start indices covering position x, [lo, hi]; appended start covers x iff
     // has_app() && x >= last.
     __host__ __device__ __forceinline__ void cover(int64_t x, int64_t& lo, int64_t& hi, bool& app) const {
-        int64_t t = x - bb + 1;
-        lo = t <= 0 ? 0 : (t + s - 1) / s;
-        hi = x / s;
-        if (hi > n_reg - 1) hi = n_reg - 1;
+        if (len <= 0x7fffffffLL) {  // 32-bit divisions (a 64-bit one is a ~100-instruction subroutine)
+            const int xi = (int)x, t = xi - bb + 1, nr = (int)n_reg;
+            const int l = t <= 0 ? 0 : (s == 1 ? t : (t + s - 1) / s), h = s == 1 ? xi : xi / s;
+            lo = l;
+            hi = h > nr - 1 ? nr - 1 : h;
+        } else {
+            int64_t t = x - bb + 1;
+            lo = t <= 0 ? 0 : (t + s - 1) / s;
+            hi = x / s;
+            if (hi > n_reg - 1) hi = n_reg - 1;
+        }
         app = (n > n_reg) && (x >= last);
     }
     __host__ __device__ __forceinline__ int count(int64_t x) const {
         if (len <= 0x7fffffffLL) {  // 32-bit arithmetic: the elementwise kernels call this per element
             const int xi = (int)x, t = xi - bb + 1, nr = (int)n_reg;
-            int lo = t <= 0 ? 0 : (t + s - 1) / s, hi = xi / s;
+            int lo = t <= 0 ? 0 : (s == 1 ? t : (t + s - 1) / s), hi = s == 1 ? xi : xi / s;
             if (hi > nr - 1) hi = nr - 1;
             int c = hi - lo + 1;
             if (c < 0) c = 0;

@@ -86,6 +86,41 @@ __global__ void im2col_kernel(Geom g, const float* __restrict__ X, const float* 
     }
 }
 
+// Stride-1 im2col: a block owns 128 consecutive row starts of one column start, stages their (128+bb-1) x bb window
+// (plus the multiplier term) in shared memory with row-contiguous loads — 4 cache lines per warp request instead of the
+// 32 of the thread-per-patch gather above, which is L1-wavefront bound — and then streams the bb*bb rows of `blocks`
+// out, 512 contiguous bytes per row.
+template <int IM2COL_TILE>
+__global__ void __launch_bounds__(256) im2col_s1_kernel(Geom g, const float* __restrict__ X, const float* __restrict__ L,
+                                                        float mu, float* __restrict__ blocks) {
+    extern __shared__ float win[];   // [(TILE + bb - 1)][bb + 1]
+    const int bb = g.bb, ld = bb + 1;
+    const int64_t ri0 = blockIdx.x * (int64_t)IM2COL_TILE, ci = blockIdx.y;
+    const int64_t nR = g.row.n;
+    const int np = (int)(nR - ri0 < IM2COL_TILE ? nR - ri0 : IM2COL_TILE);   // patches of this tile
+    const int wrows = np + bb - 1;
+    for (int e = threadIdx.x; e < wrows * bb; e += blockDim.x) {
+        const int wr = e / bb, wc = e - wr * bb;
+        const int64_t src = (ri0 + wr) * g.C + ci + wc;
+        float v = __ldg(X + src);
+        if (L) v = __fadd_rn(v, __fdiv_rn(__ldg(L + src), mu));
+        win[wr * ld + wc] = v;
+    }
+    __syncthreads();
+    const int m = threadIdx.x % IM2COL_TILE, h = threadIdx.x / IM2COL_TILE, nh = blockDim.x / IM2COL_TILE;
+    if (m >= np) return;
+    float* dst = blocks + ci * nR + ri0 + m;
+    for (int j = 0; j < bb; ++j) {                               // element k = i + bb*j = row i, column j of the patch
+        float* d = dst + (int64_t)(bb * j + h) * g.P;
+        const float* w = win + (m + h) * ld + j;
+        for (int i = h; i < bb; i += nh) {
+            __stcs(d, *w);                                       // written once, read by a later kernel: stream it
+            d += nh * g.P;
+            w += nh * ld;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // col2im: deterministic gather.  Each output element sums its covering patches in ascending patch
 // order (column start outer, row start inner) with plain fp32 adds — the order of the sequential
@@ -117,11 +152,72 @@ __device__ __forceinline__ float col2im_column(const Geom& g, const float* __res
     return sum;
 }
 
-__global__ void __launch_bounds__(256, 6) col2im_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
+// Stride-1 specialisation (the dense-overlap geometry of cfg 4/5): no appended starts, no divisions, and for interior
+// rows the BB row starts of a column start are BB loads at compile-time multiples of one pointer step — about four
+// instructions per load instead of the generic path's 28 (ncu), which is what makes the kernel HBM-bound.
+template <int BB, int JU, int MINB>
+__global__ void __launch_bounds__(256, MINB) col2im_s1_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
     __shared__ float tile[32][33];
-    int64_t r0 = blockIdx.x * 32LL, c0 = blockIdx.y * 32LL;
-    int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (32, 8)
+    const int64_t r0 = blockIdx.x * 32LL, c0 = blockIdx.y * 32LL;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (32, 8)
+    const int64_t nR = g.row.n, nC = g.col.n, P = g.P;
+    const int64_t step = 1 - P, cstep = nR - (int64_t)BB * P;
     for (int cc = ty; cc < 32; cc += 8) {
+        const int64_t r = r0 + tx, c = c0 + cc;
+        float sum = 0.0f;
+        if (r < g.R && c < g.C) {
+            const int64_t rlo = r - (BB - 1) > 0 ? r - (BB - 1) : 0, rhi = r < nR - 1 ? r : nR - 1;
+            const int64_t clo = c - (BB - 1) > 0 ? c - (BB - 1) : 0, chi = c < nC - 1 ? c : nC - 1;
+            const int nreg = (int)(rhi - rlo + 1), ncol = (int)(chi - clo + 1);
+            const float* pc = blocks + ((r - rlo) + (int64_t)BB * (c - clo)) * P + clo * nR + rlo;
+            if (nreg == BB) {
+                int j = 0;
+                for (; j + JU <= ncol; j += JU) {   // JU column starts = JU*BB independent loads in flight
+                    float v[JU][BB];
+#pragma unroll
+                    for (int w = 0; w < JU; ++w)
+#pragma unroll
+                        for (int u = 0; u < BB; ++u) v[w][u] = __ldg(pc + w * cstep + u * step);
+#pragma unroll
+                    for (int w = 0; w < JU; ++w)
+#pragma unroll
+                        for (int u = 0; u < BB; ++u) sum = __fadd_rn(sum, v[w][u]);
+                    pc += JU * cstep;
+                }
+                for (; j < ncol; ++j) {
+                    float v[BB];
+#pragma unroll
+                    for (int u = 0; u < BB; ++u) v[u] = __ldg(pc + u * step);
+#pragma unroll
+                    for (int u = 0; u < BB; ++u) sum = __fadd_rn(sum, v[u]);
+                    pc += cstep;
+                }
+            } else {
+                for (int j = 0; j < ncol; ++j) {
+                    const float* pr = pc;
+                    for (int u = 0; u < nreg; ++u) {
+                        sum = __fadd_rn(sum, __ldg(pr));
+                        pr += step;
+                    }
+                    pc += cstep;
+                }
+            }
+        }
+        tile[cc][tx] = sum;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int64_t r = r0 + rr, c = c0 + tx;
+        if (r < g.R && c < g.C) out[r * g.C + c] = tile[tx][rr];
+    }
+}
+
+template <int TR, int TC, int TY>
+__global__ void __launch_bounds__(TR * TY, 1536 / (TR * TY)) col2im_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
+    __shared__ float tile[TC][TR + 1];
+    int64_t r0 = blockIdx.x * (int64_t)TR, c0 = blockIdx.y * (int64_t)TC;
+    int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (TR, TY)
+    for (int cc = ty; cc < TC; cc += TY) {
         int64_t r = r0 + tx, c = c0 + cc;
         float sum = 0.0f;
         if (r < g.R && c < g.C) {
@@ -144,9 +240,10 @@ __global__ void __launch_bounds__(256, 6) col2im_kernel(Geom g, const float* __r
         tile[cc][tx] = sum;
     }
     __syncthreads();
-    for (int rr = ty; rr < 32; rr += 8) {
-        int64_t r = r0 + rr, c = c0 + tx;
-        if (r < g.R && c < g.C) out[r * g.C + c] = tile[tx][rr];
+    for (int idx = ty * TR + tx; idx < TR * TC; idx += TR * TY) {
+        const int rr = idx / TC, cc = idx % TC;
+        int64_t r = r0 + rr, c = c0 + cc;
+        if (r < g.R && c < g.C) out[r * g.C + c] = tile[cc][rr];
     }
 }
 
@@ -281,8 +378,16 @@ int lrs_im2col_f32(const float* X_dev, const float* L_dev, float mu, int64_t R, 
     if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_im2col_f32", "need 0 < bb <= min(R,C) and s > 0");
     if (!X_dev || !blocks_dev) return fail_arg("lrs_im2col_f32", "null pointer");
     if (L_dev && mu == 0.0f) return fail_arg("lrs_im2col_f32", "mu must be non-zero");
-    dim3 grid(blocks_for(g.P, 128), bb);
-    im2col_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, X_dev, L_dev, mu, blocks_dev);
+    // 256 row starts per block: measured 4.2-4.5 TB/s at cfg 4 (128: 3.9-4.3, 64: 3.3-3.5; thread-per-patch gather: 2.2)
+    constexpr int tile = 256;
+    const size_t win_bytes = (size_t)(tile + bb - 1) * (bb + 1) * sizeof(float);
+    if (s == 1 && win_bytes <= 48 * 1024 && g.col.n <= 65535) {
+        im2col_s1_kernel<tile><<<dim3(blocks_for(g.row.n, tile), (unsigned)g.col.n), 256, win_bytes, (cudaStream_t)stream>>>(
+            g, X_dev, L_dev, mu, blocks_dev);
+    } else {
+        dim3 grid(blocks_for(g.P, 128), bb);
+        im2col_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(g, X_dev, L_dev, mu, blocks_dev);
+    }
     LRS_CHECK_LAUNCH("lrs_im2col_f32");
     return LRS_OK;
 }
@@ -294,7 +399,10 @@ int lrs_col2im_accum_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, 
     if (!blocks_dev || !imout_dev) return fail_arg("lrs_col2im_accum_f32", "null pointer");
     dim3 grid(blocks_for(R, 32), blocks_for(C, 32));
     if (grid.y > 65535) return fail_arg("lrs_col2im_accum_f32", "C too large");
-    col2im_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
+    // measured at cfg 4 (B200): generic kernel 3.9 ms; stride-1 kernel 2.2-2.6 ms; two or four column starts in flight
+    // per thread, 8 blocks/SM with 32 registers, or longer row tiles (128x8, 256x4) are all slower
+    if (s == 1 && bb == 8) col2im_s1_kernel<8, 1, 6><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
+    else col2im_kernel<32, 32, 8><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
     LRS_CHECK_LAUNCH("lrs_col2im_accum_f32");
     return LRS_OK;
 }
