@@ -13,7 +13,10 @@ provides the training loop around it (:func:`dip_low_rank`, restating get_DIP_ou
 variance-based early stop :74-102) and keeps every tensor on the device.
 
 The dictionary ``trained_dictionary.mat`` is not part of the reference checkout; pass ``--dictionary`` or a
-seeded synthetic one (K atoms) is used.
+seeded synthetic one (K atoms) is used.  ``learn_dict`` trains a substitute on the patches of a clean cube
+(:mod:`lrs_pnp_dip_b200.dictlearn`) and writes it in the format the scripts load:
+
+    python -m lrs_pnp_dip_b200.drivers learn_dict --data-dir <ref>/data --image base --out trained_dictionary.mat
 """
 from __future__ import annotations
 
@@ -169,7 +172,28 @@ def main(argv=None):
             p.add_argument("--net", default="skip", choices=["skip", "1lip"])
             p.add_argument("--reference-root", required=True)
             p.add_argument("--dip-iterations", type=int, default=5000)
+    p = sub.add_parser("learn_dict")
+    p.add_argument("--data-dir", required=True)
+    p.add_argument("--image", default="base", choices=sorted(PAIRS))
+    p.add_argument("--out", required=True)
+    p.add_argument("--atoms", type=int, default=2592)
+    p.add_argument("--bb", type=int, default=36)
+    p.add_argument("--stride", type=int, default=4)
+    p.add_argument("--rounds", type=int, default=10)
+    p.add_argument("--lambda-ista", type=float, default=0.1)
+    p.add_argument("--iterations", type=int, default=40, help="ISTA iterations per round")
     a = ap.parse_args(argv)
+    if a.cmd == "learn_dict":
+        from . import dictlearn
+
+        _, clean, _ = load_case(a.data_dir, a.image)
+        Y = torch.tensor(matio.unfold_cube(clean)).cuda()
+        patches = dictlearn.training_patches(Y, a.bb, a.stride)
+        D, hist = dictlearn.learn_dictionary(patches, a.atoms, a.lambda_ista, a.iterations, a.rounds)
+        dictlearn.save_dictionary(a.out, D)
+        print(f"learned {tuple(D.shape)} dictionary from {patches.shape[1]} patches; relative error per round: "
+              + " ".join(f"{h:.4f}" for h in hist))
+        return
     noisy, clean, msk = load_case(a.data_dir, a.image, a.mask)
     bb = 36
     D = load_dictionary(a.dictionary or os.path.join(a.data_dir, "trained_dictionary.mat"), bb * bb, a.atoms)

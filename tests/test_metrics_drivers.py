@@ -88,3 +88,23 @@ def test_dip_low_rank_hook_with_stand_in_network(golden):
     sol = LRSPnP(Y, matio.unfold_mask(msk.cpu().numpy(), 128), D, prm, low_rank=hook, device=dev)
     sol.run(2)
     assert torch.isfinite(sol.X).all() and sol.X.shape == (1296, 128)
+
+
+def test_dictlearn_host_pieces(tmp_path):
+    """columnNormalise.m semantics, the .mat round trip through the drivers' loader, and the loud failure of the
+    learner without a CUDA device (no CPU fallback)."""
+    import torch
+
+    from lrs_pnp_dip_b200 import _lib, dictlearn, drivers
+
+    A = torch.tensor([[3.0, 0.0, 1.0], [4.0, 0.0, 1.0]])
+    N = dictlearn.column_normalise(A)
+    assert torch.allclose(N[:, 0], torch.tensor([0.6, 0.8])) and torch.equal(N[:, 1], torch.zeros(2))
+    assert abs(float(N[:, 2].norm()) - 1.0) < 1e-6
+    D = np.random.default_rng(0).standard_normal((16, 24)).astype(np.float32)
+    path = str(tmp_path / "trained_dictionary.mat")
+    dictlearn.save_dictionary(path, D)
+    assert np.array_equal(drivers.load_dictionary(path, 16, 24), D)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.LrsError):
+            dictlearn.learn_dictionary(torch.zeros(16, 64), 8)
