@@ -45,7 +45,8 @@ constexpr int TILE = 128;
 constexpr int NEPI = 8;                        // epilogue warps (8 measured faster than 16: the epilogue is issue-bound)
 constexpr int NCG = NEPI / 4;                  // column groups per TMEM lane quarter
 constexpr int CW = 64 / NCG;                   // columns (of a 64-column chunk) and pixels per epilogue thread
-constexpr int QPT = CW / 16;                   // 16-pixel residual quarters per epilogue thread
+constexpr int NPX = 16 / NCG;                  // pixels of every 16-pixel GEMM-B k-step owned by one epilogue thread
+static_assert(NPX == 8, "the residual epilogue moves its pixels with 8-column TMEM loads and 16-byte stores");
 constexpr int FIRST_EPI = (NEPI == 8) ? 4 : 2; // first epilogue warp (keeps warp % 4 == TMEM lane quarter)
 constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
 constexpr int MAXCHUNK = 4;                    // soft-threshold / GEMM-A pipeline: K/64 chunks of 64 atoms, K <= 256
@@ -68,6 +69,7 @@ constexpr uint32_t D_SMEM_BYTES = 64 * 1024;
 // halves, so that the soft-threshold of the first half overlaps the MMAs of the second (an N = 128 MMA with A in
 // shared memory runs at its 64-cycle MAC floor; with A in TMEM it would cost 88).  false = A from TMEM, N = 256.
 constexpr bool B_SS = true;
+static_assert(B_SS, "the TMEM-operand GEMM-B variant (v2) was removed with the shared k-step mapping");
 // residual pieces in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048 + piece*16384
 constexpr uint32_t R_SMEM_BYTES = B_SS ? 32 * 1024 : 0;
 constexpr uint32_t R_SK = 2048, R_SM = 128, R_PIECE = 16 * 1024;
@@ -95,7 +97,7 @@ constexpr uint32_t A2_SK = 2048, A2_SM = 128;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 
 struct __align__(8) Shared {
-    uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in TMEM        (4 warps)
+    uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in shared memory (NEPI warps)
     uint64_t bar_B[2];        // MMA -> epilogue: GEMM-B complete for atom half h (h = 0 only when !B_SS)      (commit)
     uint64_t bar_S[MAXCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
     uint64_t bar_A[MAXCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     if (tid == 0) {
         mbar_init(&sh.bar_B[0], 1);
         mbar_init(&sh.bar_B[1], 1);
-        for (int j = 0; j < 4; ++j) mbar_init(&sh.bar_R[j], 4);
+        for (int j = 0; j < 4; ++j) mbar_init(&sh.bar_R[j], NEPI);
         for (int j = 0; j < NCHUNK; ++j) {
             mbar_init(&sh.bar_S[j], NEPI);
             mbar_init(&sh.bar_A[j], 1);
@@ -300,18 +302,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
-                if (B_SS) {
+                {
                     const uint32_t idescB128 = make_idesc_f16(128, KH, /*b_mn_major=*/true);
                     const uint64_t descR0 = make_smem_desc(smem_u32(Rsm), /*lbo=*/R_SK, /*sbo=*/R_SM);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;   // 0,2,1,3: order of readiness
+                        for (int ks = 0; ks < 4; ++ks) {
                             if (half == 0) {
                                 long long w0 = TSTAMP();
                                 mbar_wait(&sh.bar_R[ks], par);
-                                if (DBG) dbg[1 + kk] += clock64() - w0;
+                                if (DBG) dbg[1 + ks] += clock64() - w0;
                                 tc_fence_after();
                             }
                             const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                             const uint64_t r2 = descR0 + (uint64_t)((R_PIECE + 2 * ks * R_SK) >> 4);
                             const uint32_t acc = tbase + COL_ALPHA + KH * half;
                             if (leader) {
-                                mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && kk == 0));
+                                mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && ks == 0));
                                 mma_f16_ss(acc, r2, d1, idescB128, true);
                                 mma_f16_ss(acc, r1, d2, idescB128, true);
                             }
@@ -329,28 +330,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                         if (leader) mma_commit(&sh.bar_B[half]);
                         __syncwarp();
                     }
-                } else {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        // quarters become ready in the order the epilogue threads produce them: 0,2,1,3 when a thread
-                        // owns two consecutive quarters
-                        const int ks = (QPT == 2) ? (((kk & 1) << 1) | (kk >> 1)) : kk;
-                        long long w0 = TSTAMP();
-                        mbar_wait(&sh.bar_R[ks], par);
-                        if (DBG) dbg[1 + kk] += clock64() - w0;
-                        tc_fence_after();
-                        const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI) >> 4);
-                        const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI) >> 4);
-                        const uint32_t r1 = tbase + COL_STG0 + 8 * ks, r2 = tbase + COL_STG0 + 32 + 8 * ks;
-                        if (leader) {
-                            mma_f16_ts(tbase + COL_ALPHA, r1, d1, idescB, !(it == 0 && kk == 0));
-                            mma_f16_ts(tbase + COL_ALPHA, r2, d1, idescB, true);
-                            mma_f16_ts(tbase + COL_ALPHA, r1, d2, idescB, true);
-                        }
-                        __syncwarp();
-                    }
-                    if (leader) mma_commit(&sh.bar_B[0]);
-                    __syncwarp();
                 }
                 // ---- GEMM-A: Da = state D^T, chunk by chunk as the soft-threshold epilogue releases them ----
 #pragma unroll
@@ -396,7 +375,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         const long long e_begin = TSTAMP();
         for (TileWalk tw; tw.next(plan, prm);) {
             const long long tp0 = TSTAMP();
-            // ---- tile prologue: gather my CW pixels (window columns CW/8*cg ..), mask, step constant, scale ----
+            // ---- tile prologue: gather my CW pixels, mask, step constant, scale.  Register slot c holds pixel
+            //      16*(c/8) + 8*cg + c%8 = window row c%8, column 2*(c/8) + cg: every 16-pixel GEMM-B k-step is shared by
+            //      the two column groups, so that all warps finish quarter ks together and its MMAs start early ----
             int64_t ci = tw.ci, ri = (int64_t)tw.rb * TILE + m;
             int64_t p = ci * nR + ri;
             const bool valid = ri < nR && p >= prm.p_begin && p < prm.p_end;
@@ -413,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             float amax = 0.f, nsum = 0.f;
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
-                const int64_t src = (rs + (c & 7)) * C + cs + (CW / 8) * cg + (c >> 3);
+                const int64_t src = (rs + (c & 7)) * C + cs + NCG * (c >> 3) + cg;
                 float v = __ldg(prm.X + src);
                 if (prm.L) v = __fadd_rn(v, __fdiv_rn(__ldg(prm.L + src), prm.mu1));
                 const bool ok = __ldg(prm.Yobs + src) != 0.0f;
@@ -421,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 if (ok) {
                     mbits |= 1u << c;
                     amax = fmaxf(amax, fabsf(v));
-                    nsum += sh.rn[CW * cg + c];
+                    nsum += sh.rn[16 * (c >> 3) + NPX * cg + (c & 7)];
                 }
             }
             sh.xmax[cg][m] = amax;
@@ -463,19 +444,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     tc_fence_after();
                 }
 #pragma unroll
-                for (int qq = 0; qq < QPT; ++qq) {
-                    const int ks = QPT * cg + qq;            // pixel quarter = GEMM-B k-step
-                    uint32_t p1[8], p2[8];
+                for (int ks = 0; ks < 4; ++ks) {             // pixel quarter = GEMM-B k-step; my NPX pixels of it
+                    uint32_t p1[NPX / 2], p2[NPX / 2];
                     if (it > 0) {
-                        uint32_t a0[16], a1[16];
-                        tmem_ld16(lane_addr + COL_ACC + 16 * ks, a0);
-                        tmem_ld16(lane_addr + COL_ACC + 64 + 16 * ks, a1);
+                        // (prefetching the next quarter's accumulators here was measured: 664 ms vs 654 ms — the extra
+                        //  registers spill inside the iteration loop)
+                        uint32_t b0[NPX], b1[NPX];
+                        tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
+                        tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int e = 16 * qq + 2 * c;
-                            const uint64_t sm2 = add2(pk2(__uint_as_float(a0[2 * c]), __uint_as_float(a0[2 * c + 1])),
-                                                      pk2(__uint_as_float(a1[2 * c]), __uint_as_float(a1[2 * c + 1])));
+                        for (int c = 0; c < NPX / 2; ++c) {
+                            const int e = NPX * ks + 2 * c;
+                            const uint64_t sm2 = add2(pk2(__uint_as_float(b0[2 * c]), __uint_as_float(b0[2 * c + 1])),
+                                                      pk2(__uint_as_float(b1[2 * c]), __uint_as_float(b1[2 * c + 1])));
                             float r0, r1;
                             upk2(fma2(nc2, sm2, pk2(ysc[e], ysc[e + 1])), r0, r1);
                             r0 = ((mbits >> e) & 1u) ? r0 : 0.f;
@@ -484,27 +466,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int e = 16 * qq + 2 * c;
+                        for (int c = 0; c < NPX / 2; ++c) {
+                            const int e = NPX * ks + 2 * c;
                             float r0 = ((mbits >> e) & 1u) ? ysc[e] : 0.f;
                             float r1 = ((mbits >> (e + 1)) & 1u) ? ysc[e + 1] : 0.f;
                             split_pair(r0, r1, p1[c], p2[c]);
                         }
                     }
-                    if (B_SS) {
-                        // 16 pixels = k-groups 2ks, 2ks+1 of my row m: two 16-byte stores per piece (a warp covers 512
-                        // contiguous bytes per store: conflict-free), then publish to the async proxy
-                        uint8_t* rrow = Rsm + (uint32_t)(m >> 3) * R_SM + (uint32_t)(m & 7) * 16 + (uint32_t)(2 * ks) * R_SK;
-                        *reinterpret_cast<uint4*>(rrow) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                        *reinterpret_cast<uint4*>(rrow + R_SK) = make_uint4(p1[4], p1[5], p1[6], p1[7]);
-                        *reinterpret_cast<uint4*>(rrow + R_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                        *reinterpret_cast<uint4*>(rrow + R_PIECE + R_SK) = make_uint4(p2[4], p2[5], p2[6], p2[7]);
-                        fence_async_smem();
-                    } else {
-                        tmem_st8(lane_addr + COL_STG0 + 8 * ks, p1);
-                        tmem_st8(lane_addr + COL_STG0 + 32 + 8 * ks, p2);
-                        tmem_wait_st();
-                    }
+                    // my 8 pixels = k-group 2ks + cg of my row m: one 16-byte store per piece (a warp covers 512 contiguous
+                    // bytes per store: conflict-free), then publish to the async proxy
+                    uint8_t* rrow = Rsm + (uint32_t)(m >> 3) * R_SM + (uint32_t)(m & 7) * 16 + (uint32_t)(NCG * ks + cg) * R_SK;
+                    *reinterpret_cast<uint4*>(rrow) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                    *reinterpret_cast<uint4*>(rrow + R_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                    fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sh.bar_R[ks]);
@@ -579,15 +553,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 uint32_t a0[CW], a1[CW];
                 mbar_wait(&sh.bar_A[NCHUNK - 1], (gi - 1) & 1);
                 tc_fence_after();
-                tmem_ldN<CW>(lane_addr + COL_ACC + CW * cg, a0);
-                tmem_ldN<CW>(lane_addr + COL_ACC + 64 + CW * cg, a1);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    tmem_ld8(lane_addr + COL_ACC + 16 * q4 + NPX * cg, a0 + NPX * q4);
+                    tmem_ld8(lane_addr + COL_ACC + 64 + 16 * q4 + NPX * cg, a1 + NPX * q4);
+                }
                 tmem_wait_ld();
                 tc_fence_before();   // order these loads before the next tile's MMAs (via bar_R)
                 const float sc = up * inv_a / (S_ALPHA * S_D);
                 if (valid) {
 #pragma unroll
                     for (int c = 0; c < CW; ++c)
-                        __stcs(prm.phi + (int64_t)(CW * cg + c) * total + pi,
+                        __stcs(prm.phi + (int64_t)(16 * (c >> 3) + NPX * cg + (c & 7)) * total + pi,
                                (__uint_as_float(a0[c]) + __uint_as_float(a1[c])) * sc);   // streaming: keep the cube in L2
                 }
             }
