@@ -364,7 +364,9 @@ size_t lrs_ista_workspace_bytes(int n, int K, int64_t P) {
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     const size_t s1 = (size_t)lrs::ista_splits(n, P, K) * n, s2 = (size_t)lrs::ista_splits(K, P, n) * K;
     const size_t part = (s1 > (size_t)n || s2 > (size_t)K) ? al((s1 > s2 ? s1 : s2) * (size_t)P * 4) : 0;
-    return 2 * al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4) + part;
+    const size_t simt = 2 * al((size_t)K * P * 4) + al((size_t)n * P * 4) + 2 * al((size_t)P * 4) + part;
+    const size_t tcb = lrs::ista_tc_workspace_bytes(n, K, P);   // fp16 operand pieces of the tensor-core engine
+    return simt > tcb ? simt : tcb;
 }
 
 int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
@@ -388,6 +390,9 @@ int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, cons
         return LRS_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (denoiser == LRS_DENOISE_SOFT && ista_tc_shape_ok(n, K, P) && ista_tc_enabled())
+        return ista_tc_run(blocks_dev, blocks_copy_dev, D_dev, a_dev, lambda_ista, Nit, n, K, P, coefs_dev, phi_z_dev,
+                           workspace_dev, workspace_bytes, st);
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     char* w = (char*)workspace_dev;
     float* A = (float*)w;

@@ -1,0 +1,421 @@
+// Tensor-core engine of the explicit ISTA path (lrs_ista_pnp_f32 with the soft denoiser) for the LARGE-PATCH regime of
+// the bundled configurations: n = bb^2 = 1296 pixels, K ~ 2592 atoms, P = 144 patches (main_LRS_PnP.py:131-149,
+// 270-303; ista.m:13-24).  There the dictionary (13 MB) does not fit on chip and the two products of an iteration,
+//     D alpha  [n x P] = D [n x K]  alpha [K x P]          and          D^T r  [K x P] = D^T [K x n]  r [n x P],
+// are tall-skinny GEMMs against a 144-column operand.  Each runs as ONE split-K launch of tcgen05 MMAs (M = 128 rows
+// per CTA, N = P <= 256, fp32 accumulators in TMEM) followed by a small reduce kernel that adds the split-K slices in a
+// fixed order and applies the fused epilogue (mask + residual, or gradient step + soft threshold).
+//
+// fp32 accuracy comes from the same 3-pass fp16 operand split as the fused engine (sparse_fused_tc.cu):
+//   x = x1 + x2, x1 = fp16(x), x2 = fp16(x - x1);   a b ~ a1 b1 + a2 b1 + a1 b2   (fp32 accumulate).
+// The pieces of D (and of D^T, so that both products read a K-major A operand) are made once per call; the pieces of
+// alpha and r are written by the reduce kernels.  Every operand is normalised by an exact power of two first — D by
+// its largest entry, every patch column by its largest observed value — so the fp16 pieces are well scaled whatever
+// the scale of the data, and the products are scaled back exactly in the reduce kernels.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace lrs {
+using namespace tc;
+
+namespace {
+
+constexpr int TG_BM = 128;         // rows of the A operand per CTA (TMEM lanes)
+constexpr int TG_BK = 64;          // k per pipeline stage (4 MMA k-steps)
+constexpr int TG_THREADS = 128;
+constexpr float TS_D = 4.0f;       // D pieces  = fp16(4 sd D)
+constexpr float TS_R = 0.25f;      // r pieces  = fp16(r' / 4)     (TS_D * TS_R = 1)
+constexpr uint32_t A_PIECE = TG_BM * TG_BK * 2;     // 16 KB: [8 k-groups][128 rows][8 halves]
+
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ void split_h(float x, __half& h1, __half& h2) {
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(x - __half2float(h1));
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// max |x| as float bits (non-negative floats order like their bit patterns)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float pow2_down_scale(const unsigned* dmax_bits) {   // sd: sd * max|D| in [0.5, 1)
+    const float dmax = __uint_as_float(*dmax_bits);
+    int ex = 0;
+    if (dmax > 0.f) (void)frexpf(dmax, &ex);
+    return ldexpf(1.0f, -ex);
+}
+
+// D [n, K] -> fp16 pieces of 4 sd D, as A operand of D alpha ([2][Mp1][Kp1], rows = pixels) and of D^T r
+// ([2][Mp2][Kp2], rows = atoms); the padding was zeroed by the caller.
+__global__ void dict_pieces_kernel(const float* __restrict__ D, int n, int K, const unsigned* __restrict__ dmax_bits,
+                                   __half* __restrict__ A1, int64_t Mp1, int64_t Kp1, __half* __restrict__ A2, int64_t Mp2,
+                                   int64_t Kp2) {
+    const float sc = pow2_down_scale(dmax_bits) * TS_D;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * K) return;
+    const int64_t i = e / K, k = e - i * K;
+    __half h1, h2;
+    split_h(D[e] * sc, h1, h2);
+    A1[i * Kp1 + k] = h1;
+    A1[(Mp1 + i) * Kp1 + k] = h2;
+    A2[k * Kp2 + i] = h1;
+    A2[(Mp2 + k) * Kp2 + i] = h2;
+}
+
+// Per patch column: power-of-two normalisation of the operands, the scale-back factors of both products and the ISTA
+// threshold T = lambda / (2a) (ista.m:15-17; a <= 0 marks a patch without any observed entry: coefficients stay 0).
+//   residual pieces   = fp16 split of  m .* (y - D alpha) * sR ,  sR = 2^-ex(y) / 4       (NOT yet divided by a: with a
+//                       large step constant r / a would fall into fp16's subnormal range)
+//   coefficient pieces = fp16 split of  alpha * sA ,  sA = 2^-ex(y) * 2^ex(sqrt a)          (alpha ~ y / ||d||, a ~ ||d||^2)
+__global__ void column_scales_kernel(const float* __restrict__ Y, int n, int64_t P, const unsigned* __restrict__ dmax_bits,
+                                     const float* __restrict__ a, float lambda, float* __restrict__ sA,
+                                     float* __restrict__ f1, float* __restrict__ f2, float* __restrict__ sR,
+                                     float* __restrict__ T) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float amax = 0.f;
+    for (int i = 0; i < n; ++i) amax = fmaxf(amax, fabsf(Y[(int64_t)i * P + p]));
+    int ex = 0;
+    if (amax > 0.f && amax < INFINITY) (void)frexpf(amax, &ex);
+    const float sd = pow2_down_scale(dmax_bits);
+    const float av = a[p];
+    const bool ok = av > 0.0f && av < INFINITY;
+    int ea = 0;
+    if (ok) (void)frexpf(sqrtf(av), &ea);
+    sA[p] = ldexpf(1.0f, ea - ex);
+    sR[p] = ldexpf(TS_R, -ex);
+    f1[p] = ldexpf(1.0f, ex - ea) / (sd * TS_D);                               // D alpha   = (sum of MMAs) * f1
+    f2[p] = ok ? __fdiv_rn(ldexpf(1.0f, ex) / sd, av) : 0.0f;                  // D^T r / a = (sum of MMAs) * f2   (TS_D TS_R = 1)
+    T[p] = ok ? __fdiv_rn(lambda, __fmul_rn(2.0f, av)) : 0.0f;
+}
+
+struct GemmArgs {
+    const __half* Ap;    // [2][Mp][Kp]  K-major pieces of the left operand
+    const __half* Bp;    // [2][Kp][Np]  pieces of the right operand, patch index contiguous
+    float* partial;      // [splits][M][N]
+    int64_t M, N;        // logical output size
+    int64_t Mp, Kp, Np;  // padded sizes (Mp % 128 == 0, Kp % 64 == 0, Np % 16 == 0, Np <= 256)
+    int kb_per_split;    // 64-wide k blocks per split
+    int nkb_total;       // Kp / 64
+};
+
+// partial[z] = Ap[m0 : m0+128, k-range z] * Bp[k-range z, :]   with three MMAs per 16-wide k-step.
+// Shared memory per stage: A pieces in the K-major canonical no-swizzle layout
+//     byte(m, k) = (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048          (+ piece * 16 KB)
+// and B pieces MN-major (16-byte chunks = 8 consecutive patches)
+//     byte(nn, k) = (nn%8)*2 + (k%8)*16 + (k/8)*128 + (nn/8)*1024       (+ piece * Np*128)
+template <int STAGES>
+__global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_free[STAGES];
+    __shared__ uint64_t bar_done;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t b_piece = (uint32_t)g.Np * 128u, stage_bytes = 2 * A_PIECE + 2 * b_piece;
+    const int64_t m0 = blockIdx.x * (int64_t)TG_BM;
+    const int z = blockIdx.y;
+    const int kb0 = z * g.kb_per_split;
+    const int nkb = g.nkb_total - kb0 < g.kb_per_split ? g.nkb_total - kb0 : g.kb_per_split;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_free[s], 1);
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_slot;
+    const uint32_t sbase = smem_u32(smem);
+    const int nb8 = (int)(g.Np / 8);
+
+    auto load_stage = [&](int kb, int s) {
+        const int64_t k0 = (int64_t)(kb0 + kb) * TG_BK;
+        const uint32_t sa = sbase + (uint32_t)s * stage_bytes, sb = sa + 2 * A_PIECE;
+        for (int c = tid; c < 2 * TG_BM * (TG_BK / 8); c += TG_THREADS) {      // A: 2 pieces x 128 rows x 8 chunks
+            const int piece = c >> 10, r = (c >> 3) & (TG_BM - 1), k8 = c & 7;
+            const __half* src = g.Ap + ((int64_t)piece * g.Mp + m0 + r) * g.Kp + k0 + 8 * k8;
+            cp_async16(sa + (uint32_t)piece * A_PIECE + (uint32_t)k8 * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u, src);
+        }
+        const int per_piece = TG_BK * nb8;
+        for (int c = tid; c < 2 * per_piece; c += TG_THREADS) {                // B: 2 pieces x 64 k x Np/8 chunks
+            const int piece = c >= per_piece ? 1 : 0, rem = c - piece * per_piece;
+            const int k = rem / nb8, n8 = rem - k * nb8;
+            const __half* src = g.Bp + ((int64_t)piece * g.Kp + k0 + k) * g.Np + 8 * n8;
+            cp_async16(sb + (uint32_t)piece * b_piece + (uint32_t)n8 * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(k & 7) * 16u, src);
+        }
+    };
+
+    // prologue: fill the pipeline (one commit group per stage, empty groups keep the count uniform)
+    for (int s = 0; s < STAGES; ++s) {
+        if (s < nkb) load_stage(s, s);
+        cp_async_commit();
+    }
+    const uint32_t idesc = make_idesc_f16(128, (int)g.Np, /*b_mn_major=*/true);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        cp_async_wait<STAGES - 1>();      // the group of block kb has landed (later ones may still be in flight)
+        fence_async_smem();               // generic-proxy writes (cp.async) -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            const uint32_t leader = elect_one();
+            const uint32_t sa = sbase + (uint32_t)s * stage_bytes, sb = sa + 2 * A_PIECE;
+            const uint64_t a1 = make_smem_desc(sa, /*lbo=*/2048, /*sbo=*/128), a2 = make_smem_desc(sa + A_PIECE, 2048, 128);
+            const uint64_t b1 = make_smem_desc(sb, /*lbo=*/128, /*sbo=*/1024), b2 = make_smem_desc(sb + b_piece, 128, 1024);
+#pragma unroll
+            for (int ks = 0; ks < TG_BK / 16; ++ks) {
+                const uint64_t ao = (uint64_t)((2 * ks * 2048) >> 4), bo = (uint64_t)((2 * ks * 128) >> 4);
+                if (leader) {
+                    mma_f16_ss(tbase, a1 + ao, b1 + bo, idesc, !(kb == 0 && ks == 0));
+                    mma_f16_ss(tbase, a2 + ao, b1 + bo, idesc, true);
+                    mma_f16_ss(tbase, a1 + ao, b2 + bo, idesc, true);
+                }
+            }
+            if (leader) mma_commit(&bar_free[s]);
+            __syncwarp();
+        }
+        // refill this stage with block kb + STAGES once its MMAs have drained
+        if (kb + STAGES < nkb) {
+            mbar_wait(&bar_free[s], (uint32_t)((kb / STAGES) & 1));
+            load_stage(kb + STAGES, s);
+        }
+        cp_async_commit();
+    }
+    if (warp == 0) {
+        const uint32_t leader = elect_one();
+        if (leader) mma_commit(&bar_done);
+        __syncwarp();
+    }
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    // epilogue: TMEM lane = output row; each thread writes its row's N partial sums
+    {
+        const int64_t m = m0 + 32 * warp + lane;
+        float* dst = g.partial + ((int64_t)z * g.M + (m < g.M ? m : 0)) * g.N;
+        const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
+        const bool vec = (g.N % 4 == 0);
+        for (int c0 = 0; c0 < (int)g.Np; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(lane_addr + (uint32_t)c0, v);
+            tmem_wait_ld();
+            if (m < g.M) {
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (c0 + j < g.N)
+                            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < g.N) dst[c0 + j] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// ---- reduce kernels: add the split-K slices in a fixed order, apply the epilogue, emit the next operand's pieces ----
+__device__ __forceinline__ float reduce_slices(const float* __restrict__ partial, int splits, int64_t MN, int64_t e) {
+    float s = partial[e];
+    for (int zz = 1; zz < splits; ++zz) s += partial[(int64_t)zz * MN + e];
+    return s;
+}
+
+// r = m .* (y - D alpha)  -> r pieces (the division by the step constant happens after D^T r, in f2)
+__global__ void reduce_residual_kernel(const float* __restrict__ partial, int splits, int64_t n, int64_t P, int64_t Np,
+                                       int64_t Kp2, const float* __restrict__ Y, const float* __restrict__ BC,
+                                       const float* __restrict__ f1, const float* __restrict__ sR,
+                                       __half* __restrict__ B2p) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n * P) return;
+    const int64_t i = e / P, p = e - i * P;
+    const float da = reduce_slices(partial, splits, n * P, e) * f1[p];
+    const float v = (BC[e] != 0.0f) ? (Y[e] - da) : 0.0f;
+    __half h1, h2;
+    split_h(v * sR[p], h1, h2);
+    B2p[i * Np + p] = h1;
+    B2p[(Kp2 + i) * Np + p] = h2;
+}
+
+// alpha <- soft(alpha + D^T r, T)  (ista.m:21-23) -> alpha (fp32 state) and its pieces
+__global__ void reduce_gradient_kernel(const float* __restrict__ partial, int splits, int64_t K, int64_t P, int64_t Np,
+                                       int64_t Kp1, float* __restrict__ A, const float* __restrict__ T,
+                                       const float* __restrict__ f2, const float* __restrict__ sA, __half* __restrict__ B1p) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= K * P) return;
+    const int64_t k = e / P, p = e - k * P;
+    const float c = reduce_slices(partial, splits, K * P, e) * f2[p];
+    const float x = soft_thr(A[e] + c, T[p]);
+    A[e] = x;
+    __half h1, h2;
+    split_h(x * sA[p], h1, h2);
+    B1p[k * Np + p] = h1;
+    B1p[(Kp1 + k) * Np + p] = h2;
+}
+
+// Phi_z = D alpha (full dictionary, main_LRS_PnP.py:294)
+__global__ void reduce_store_kernel(const float* __restrict__ partial, int splits, int64_t n, int64_t P,
+                                    const float* __restrict__ f1, float* __restrict__ phi) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n * P) return;
+    phi[e] = reduce_slices(partial, splits, n * P, e) * f1[e % P];
+}
+
+struct Plan {
+    int64_t Mp1, Kp1, Mp2, Kp2, Np;
+    int S1, kb1, S2, kb2;   // splits and k blocks per split of both products
+    size_t off_A, off_vec, off_dmax, off_A1, off_A2, off_B1, off_B2, off_part, total;
+};
+
+size_t al256(size_t b) { return (b + 255) / 256 * 256; }
+
+void choose_splits(int64_t Mp, int64_t Kp, int sms, int& S, int& kb_per) {
+    const int mt = (int)(Mp / TG_BM), nkb = (int)(Kp / TG_BK);
+    int s = sms / mt;
+    if (s < 1) s = 1;
+    if (s > nkb) s = nkb;
+    kb_per = (nkb + s - 1) / s;
+    S = (nkb + kb_per - 1) / kb_per;
+}
+
+Plan make_plan(int n, int K, int64_t P, int sms) {
+    Plan pl;
+    pl.Mp1 = round_up(n, TG_BM);
+    pl.Kp1 = round_up(K, TG_BK);
+    pl.Mp2 = round_up(K, TG_BM);
+    pl.Kp2 = round_up(n, TG_BK);
+    pl.Np = round_up(P, 16);
+    choose_splits(pl.Mp1, pl.Kp1, sms, pl.S1, pl.kb1);
+    choose_splits(pl.Mp2, pl.Kp2, sms, pl.S2, pl.kb2);
+    size_t o = 0;
+    pl.off_A = o;
+    o += al256((size_t)K * P * 4);
+    pl.off_vec = o;
+    o += 5 * al256((size_t)P * 4);
+    pl.off_dmax = o;
+    o += 256;
+    pl.off_A1 = o;
+    o += al256((size_t)2 * pl.Mp1 * pl.Kp1 * 2);
+    pl.off_A2 = o;
+    o += al256((size_t)2 * pl.Mp2 * pl.Kp2 * 2);
+    pl.off_B1 = o;
+    o += al256((size_t)2 * pl.Kp1 * pl.Np * 2);
+    pl.off_B2 = o;
+    o += al256((size_t)2 * pl.Kp2 * pl.Np * 2);
+    pl.off_part = o;
+    const size_t p1 = (size_t)pl.S1 * n * P * 4, p2 = (size_t)pl.S2 * K * P * 4;
+    o += al256(p1 > p2 ? p1 : p2);
+    pl.total = o;
+    return pl;
+}
+
+constexpr int PLAN_SMS = 148;   // the workspace size must not depend on the device that later runs the call
+
+}  // namespace
+
+// Shapes the engine takes: a patch count that fits one MMA (N <= 256) and operands big enough to be worth the pieces.
+bool ista_tc_shape_ok(int n, int K, int64_t P) { return P >= 8 && P <= 256 && n >= 128 && K >= 128; }
+
+size_t ista_tc_workspace_bytes(int n, int K, int64_t P) { return ista_tc_shape_ok(n, K, P) ? make_plan(n, K, P, PLAN_SMS).total : 0; }
+
+bool ista_tc_enabled() {
+    const char* e = getenv("LRS_ISTA_ENGINE");   // "simt" forces the FFMA engine (tests compare the two)
+    if (e && e[0] == 's') return false;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    return major == 10;
+}
+
+template <int STAGES>
+static int launch_tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
+    const size_t smem = (size_t)STAGES * (2 * A_PIECE + 2 * (size_t)g.Np * 128);
+    int rc = check_cuda(fn, cudaFuncSetAttribute(tc_gemm_splitk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc != LRS_OK) return rc;
+    dim3 grid((unsigned)(g.Mp / TG_BM), (unsigned)splits);
+    tc_gemm_splitk_kernel<STAGES><<<grid, TG_THREADS, smem, st>>>(g);
+    note_launch();
+    return check_cuda(fn, cudaGetLastError());
+}
+
+static int tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
+    const size_t stage = 2 * A_PIECE + 2 * (size_t)g.Np * 128;
+    return 3 * stage <= 220 * 1024 ? launch_tc_gemm<3>(fn, g, splits, st) : launch_tc_gemm<2>(fn, g, splits, st);
+}
+
+int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, const float* a, float lambda, int Nit,
+                int n, int K, int64_t P, float* coefs, float* phi, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const char* fn = "lrs_ista_pnp_f32";
+    const Plan pl = make_plan(n, K, P, PLAN_SMS);
+    if (ws_bytes < pl.total) {
+        set_error(std::string(fn) + ": workspace smaller than lrs_ista_workspace_bytes()");
+        return LRS_E_WORKSPACE;
+    }
+    char* w = (char*)ws;
+    float* A = (float*)(w + pl.off_A);
+    float* vec = (float*)(w + pl.off_vec);
+    const size_t vs = al256((size_t)P * 4) / 4;
+    float *sR = vec, *T = vec + vs, *sA = vec + 2 * vs, *f1 = vec + 3 * vs, *f2 = vec + 4 * vs;
+    unsigned* dmax = (unsigned*)(w + pl.off_dmax);
+    __half* A1 = (__half*)(w + pl.off_A1);
+    __half* A2 = (__half*)(w + pl.off_A2);
+    __half* B1 = (__half*)(w + pl.off_B1);
+    __half* B2 = (__half*)(w + pl.off_B2);
+    float* part = (float*)(w + pl.off_part);
+
+    // x0 = 0 (ista.m:14), zero padding of every piece buffer, max |D|
+    int rc = check_cuda(fn, cudaMemsetAsync(w + pl.off_A, 0, pl.off_part - pl.off_A, st));
+    if (rc != LRS_OK) return rc;
+    const int64_t nD = (int64_t)n * K;
+    absmax_kernel<<<(unsigned)((nD + 1023) / 1024 < 592 ? (nD + 1023) / 1024 : 592), 256, 0, st>>>(D, nD, dmax);
+    LRS_CHECK_LAUNCH(fn);
+    dict_pieces_kernel<<<(unsigned)((nD + 255) / 256), 256, 0, st>>>(D, n, K, dmax, A1, pl.Mp1, pl.Kp1, A2, pl.Mp2, pl.Kp2);
+    LRS_CHECK_LAUNCH(fn);
+    column_scales_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(blocks, n, P, dmax, a, lambda, sA, f1, f2, sR, T);
+    LRS_CHECK_LAUNCH(fn);
+
+    GemmArgs g1{A1, B1, part, n, P, pl.Mp1, pl.Kp1, pl.Np, pl.kb1, (int)(pl.Kp1 / TG_BK)};   // D alpha
+    GemmArgs g2{A2, B2, part, K, P, pl.Mp2, pl.Kp2, pl.Np, pl.kb2, (int)(pl.Kp2 / TG_BK)};   // D^T r
+    const unsigned eb1 = (unsigned)(((int64_t)n * P + 255) / 256), eb2 = (unsigned)(((int64_t)K * P + 255) / 256);
+    for (int it = 0; it < Nit; ++it) {
+        if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
+        reduce_residual_kernel<<<eb1, 256, 0, st>>>(part, pl.S1, n, P, pl.Np, pl.Kp2, blocks, blocks_copy, f1, sR, B2);
+        LRS_CHECK_LAUNCH(fn);
+        if ((rc = tc_gemm(fn, g2, pl.S2, st)) != LRS_OK) return rc;
+        reduce_gradient_kernel<<<eb2, 256, 0, st>>>(part, pl.S2, K, P, pl.Np, pl.Kp1, A, T, f2, sA, B1);
+        LRS_CHECK_LAUNCH(fn);
+    }
+    if (phi) {
+        if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
+        reduce_store_kernel<<<eb1, 256, 0, st>>>(part, pl.S1, n, P, f1, phi);
+        LRS_CHECK_LAUNCH(fn);
+    }
+    if (coefs) {
+        rc = check_cuda(fn, cudaMemcpyAsync(coefs, A, (size_t)K * P * 4, cudaMemcpyDeviceToDevice, st));
+        if (rc != LRS_OK) return rc;
+    }
+    return LRS_OK;
+}
+
+}  // namespace lrs
