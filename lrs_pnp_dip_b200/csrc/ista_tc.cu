@@ -38,11 +38,15 @@ __device__ __forceinline__ void split_h(float x, __half& h1, __half& h2) {
     h2 = __float2half_rn(x - __half2float(h1));
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // max |x| as float bits (non-negative floats order like their bit patterns)
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
@@ -60,21 +64,29 @@ __device__ __forceinline__ float pow2_down_scale(const unsigned* dmax_bits) {   
     return ldexpf(1.0f, -ex);
 }
 
-// D [n, K] -> fp16 pieces of 4 sd D, as A operand of D alpha ([2][Mp1][Kp1], rows = pixels) and of D^T r
-// ([2][Mp2][Kp2], rows = atoms); the padding was zeroed by the caller.
+// Operand pieces live in global memory as the exact images of the shared-memory stages, so that a stage is ONE
+// contiguous bulk copy:
+//   A tile (128 rows x 64 k), 32 KB:  halves  [piece][k/8][row][k%8]                 tile index = mtile * (Kp/64) + kblock
+//   B tile (64 k x Np patches):       halves  [piece][p/8][k][p%8]                   tile index = kblock
+__device__ __forceinline__ int64_t a_tile_offset(int64_t row, int64_t k, int64_t nkb) {
+    return (((row >> 7) * nkb + (k >> 6)) << 14) + (((k & 63) >> 3) << 10) + ((row & 127) << 3) + (k & 7);
+}
+
+// D [n, K] -> fp16 pieces of 4 sd D, as A operand of D alpha (rows = pixels, k = atoms) and of D^T r (rows = atoms,
+// k = pixels); the padding was zeroed by the caller.
 __global__ void dict_pieces_kernel(const float* __restrict__ D, int n, int K, const unsigned* __restrict__ dmax_bits,
-                                   __half* __restrict__ A1, int64_t Mp1, int64_t Kp1, __half* __restrict__ A2, int64_t Mp2,
-                                   int64_t Kp2) {
+                                   __half* __restrict__ A1, int64_t nkb1, __half* __restrict__ A2, int64_t nkb2) {
     const float sc = pow2_down_scale(dmax_bits) * TS_D;
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= (int64_t)n * K) return;
     const int64_t i = e / K, k = e - i * K;
     __half h1, h2;
     split_h(D[e] * sc, h1, h2);
-    A1[i * Kp1 + k] = h1;
-    A1[(Mp1 + i) * Kp1 + k] = h2;
-    A2[k * Kp2 + i] = h1;
-    A2[(Mp2 + k) * Kp2 + i] = h2;
+    const int64_t o1 = a_tile_offset(i, k, nkb1), o2 = a_tile_offset(k, i, nkb2);
+    A1[o1] = h1;
+    A1[o1 + 8192] = h2;
+    A2[o2] = h1;
+    A2[o2 + 8192] = h2;
 }
 
 // Per patch column: power-of-two normalisation of the operands, the scale-back factors of both products and the ISTA
@@ -105,8 +117,8 @@ __global__ void column_scales_kernel(const float* __restrict__ Y, int n, int64_t
 }
 
 struct GemmArgs {
-    const __half* Ap;    // [2][Mp][Kp]  K-major pieces of the left operand
-    const __half* Bp;    // [2][Kp][Np]  pieces of the right operand, patch index contiguous
+    const __half* Ap;    // A tiles (see above), (Mp/128) x (Kp/64) of them
+    const __half* Bp;    // B tiles, Kp/64 of them
     float* partial;      // [splits][M][N]
     int64_t M, N;        // logical output size
     int64_t Mp, Kp, Np;  // padded sizes (Mp % 128 == 0, Kp % 64 == 0, Np % 16 == 0, Np <= 256)
@@ -114,26 +126,31 @@ struct GemmArgs {
     int nkb_total;       // Kp / 64
 };
 
-// partial[z] = Ap[m0 : m0+128, k-range z] * Bp[k-range z, :]   with three MMAs per 16-wide k-step.
-// Shared memory per stage: A pieces in the K-major canonical no-swizzle layout
+// partial[z] = A[m0 : m0+128, k-range z] * B[k-range z, :]   with three MMAs per 16-wide k-step.
+// A stage in shared memory (K-major canonical no-swizzle layout, LBO = 2048 between k-groups, SBO = 128 between row groups):
 //     byte(m, k) = (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048          (+ piece * 16 KB)
-// and B pieces MN-major (16-byte chunks = 8 consecutive patches)
+// B stage (MN-major: 16-byte chunks = 8 consecutive patches, LBO = 128 between k-groups, SBO = 1024 between patch groups):
 //     byte(nn, k) = (nn%8)*2 + (k%8)*16 + (k/8)*128 + (nn/8)*1024       (+ piece * Np*128)
+// Warp 0 issues the MMAs, lane 0 of warp 1 drives the bulk copies, all four warps drain TMEM at the end.
 template <int STAGES>
 __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar_full[STAGES];
     __shared__ uint64_t bar_free[STAGES];
     __shared__ uint64_t bar_done;
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t b_piece = (uint32_t)g.Np * 128u, stage_bytes = 2 * A_PIECE + 2 * b_piece;
+    const uint32_t b_piece = (uint32_t)g.Np * 128u, a_bytes = 2 * A_PIECE, b_bytes = 2 * b_piece, stage_bytes = a_bytes + b_bytes;
     const int64_t m0 = blockIdx.x * (int64_t)TG_BM;
     const int z = blockIdx.y;
     const int kb0 = z * g.kb_per_split;
     const int nkb = g.nkb_total - kb0 < g.kb_per_split ? g.nkb_total - kb0 : g.kb_per_split;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bar_free[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_free[s], 1);
+        }
         mbar_init(&bar_done, 1);
         mbar_fence_init();
     }
@@ -143,40 +160,28 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     tc_fence_after();
     const uint32_t tbase = tmem_base_slot;
     const uint32_t sbase = smem_u32(smem);
-    const int nb8 = (int)(g.Np / 8);
 
-    auto load_stage = [&](int kb, int s) {
-        const int64_t k0 = (int64_t)(kb0 + kb) * TG_BK;
-        const uint32_t sa = sbase + (uint32_t)s * stage_bytes, sb = sa + 2 * A_PIECE;
-        for (int c = tid; c < 2 * TG_BM * (TG_BK / 8); c += TG_THREADS) {      // A: 2 pieces x 128 rows x 8 chunks
-            const int piece = c >> 10, r = (c >> 3) & (TG_BM - 1), k8 = c & 7;
-            const __half* src = g.Ap + ((int64_t)piece * g.Mp + m0 + r) * g.Kp + k0 + 8 * k8;
-            cp_async16(sa + (uint32_t)piece * A_PIECE + (uint32_t)k8 * 2048u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u, src);
+    if (warp == 1 && lane == 0) {
+        // ---- producer: one 32 KB bulk copy for the A stage, one for the B stage ----
+        const __half* atile = g.Ap + (((int64_t)blockIdx.x * g.nkb_total + kb0) << 14);
+        const __half* btile = g.Bp + (int64_t)kb0 * (b_bytes / 2);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&bar_free[s], (uint32_t)(((kb / STAGES) - 1) & 1));   // its MMAs have drained
+            const uint32_t sa = sbase + (uint32_t)s * stage_bytes;
+            mbar_expect_tx(&bar_full[s], stage_bytes);
+            bulk_g2s(sa, atile + ((int64_t)kb << 14), a_bytes, &bar_full[s]);
+            bulk_g2s(sa + a_bytes, btile + (int64_t)kb * (b_bytes / 2), b_bytes, &bar_full[s]);
         }
-        const int per_piece = TG_BK * nb8;
-        for (int c = tid; c < 2 * per_piece; c += TG_THREADS) {                // B: 2 pieces x 64 k x Np/8 chunks
-            const int piece = c >= per_piece ? 1 : 0, rem = c - piece * per_piece;
-            const int k = rem / nb8, n8 = rem - k * nb8;
-            const __half* src = g.Bp + ((int64_t)piece * g.Kp + k0 + k) * g.Np + 8 * n8;
-            cp_async16(sb + (uint32_t)piece * b_piece + (uint32_t)n8 * 1024u + (uint32_t)(k >> 3) * 128u + (uint32_t)(k & 7) * 16u, src);
-        }
-    };
-
-    // prologue: fill the pipeline (one commit group per stage, empty groups keep the count uniform)
-    for (int s = 0; s < STAGES; ++s) {
-        if (s < nkb) load_stage(s, s);
-        cp_async_commit();
-    }
-    const uint32_t idesc = make_idesc_f16(128, (int)g.Np, /*b_mn_major=*/true);
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        cp_async_wait<STAGES - 1>();      // the group of block kb has landed (later ones may still be in flight)
-        fence_async_smem();               // generic-proxy writes (cp.async) -> visible to the tensor core's async proxy
-        __syncthreads();
-        if (warp == 0) {
+    } else if (warp == 0) {
+        // ---- MMA issuer ----
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(128, (int)g.Np, /*b_mn_major=*/true);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
-            const uint32_t leader = elect_one();
-            const uint32_t sa = sbase + (uint32_t)s * stage_bytes, sb = sa + 2 * A_PIECE;
+            const uint32_t sa = sbase + (uint32_t)s * stage_bytes, sb = sa + a_bytes;
             const uint64_t a1 = make_smem_desc(sa, /*lbo=*/2048, /*sbo=*/128), a2 = make_smem_desc(sa + A_PIECE, 2048, 128);
             const uint64_t b1 = make_smem_desc(sb, /*lbo=*/128, /*sbo=*/1024), b2 = make_smem_desc(sb + b_piece, 128, 1024);
 #pragma unroll
@@ -191,18 +196,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
             if (leader) mma_commit(&bar_free[s]);
             __syncwarp();
         }
-        // refill this stage with block kb + STAGES once its MMAs have drained
-        if (kb + STAGES < nkb) {
-            mbar_wait(&bar_free[s], (uint32_t)((kb / STAGES) & 1));
-            load_stage(kb + STAGES, s);
-        }
-        cp_async_commit();
-    }
-    if (warp == 0) {
-        const uint32_t leader = elect_one();
         if (leader) mma_commit(&bar_done);
         __syncwarp();
     }
+    __syncwarp();
     mbar_wait(&bar_done, 0);
     tc_fence_after();
     // epilogue: TMEM lane = output row; each thread writes its row's N partial sums
@@ -236,42 +233,70 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
 }
 
 // ---- reduce kernels: add the split-K slices in a fixed order, apply the epilogue, emit the next operand's pieces ----
-__device__ __forceinline__ float reduce_slices(const float* __restrict__ partial, int splits, int64_t MN, int64_t e) {
-    float s = partial[e];
-    for (int zz = 1; zz < splits; ++zz) s += partial[(int64_t)zz * MN + e];
-    return s;
+// One thread owns 8 consecutive patches of one row, i.e. one 16-byte chunk of each piece of the B tile image.
+__device__ __forceinline__ void reduce8(const float* __restrict__ partial, int splits, int64_t MN, int64_t e0, int cnt,
+                                        float (&s)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = j < cnt ? partial[e0 + j] : 0.f;
+    for (int zz = 1; zz < splits; ++zz) {
+        const float* q = partial + (int64_t)zz * MN + e0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < cnt) s[j] += q[j];
+    }
+}
+__device__ __forceinline__ void store_pieces8(__half* __restrict__ Bp, int64_t row, int64_t n8, int64_t Np, const float (&v)[8]) {
+    uint32_t w1[4], w2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __half a1, a2, b1, b2;
+        split_h(v[2 * j], a1, a2);
+        split_h(v[2 * j + 1], b1, b2);
+        w1[j] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
+        w2[j] = (uint32_t)__half_as_ushort(a2) | ((uint32_t)__half_as_ushort(b2) << 16);
+    }
+    __half* t = Bp + (row >> 6) * (2 * Np * 64) + n8 * 512 + (row & 63) * 8;   // k block, patch group, k within the block
+    *reinterpret_cast<uint4*>(t) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    *reinterpret_cast<uint4*>(t + Np * 64) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
 }
 
 // r = m .* (y - D alpha)  -> r pieces (the division by the step constant happens after D^T r, in f2)
 __global__ void reduce_residual_kernel(const float* __restrict__ partial, int splits, int64_t n, int64_t P, int64_t Np,
-                                       int64_t Kp2, const float* __restrict__ Y, const float* __restrict__ BC,
+                                       const float* __restrict__ Y, const float* __restrict__ BC,
                                        const float* __restrict__ f1, const float* __restrict__ sR,
                                        __half* __restrict__ B2p) {
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= n * P) return;
-    const int64_t i = e / P, p = e - i * P;
-    const float da = reduce_slices(partial, splits, n * P, e) * f1[p];
-    const float v = (BC[e] != 0.0f) ? (Y[e] - da) : 0.0f;
-    __half h1, h2;
-    split_h(v * sR[p], h1, h2);
-    B2p[i * Np + p] = h1;
-    B2p[(Kp2 + i) * Np + p] = h2;
+    const int64_t nb8 = Np / 8, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * nb8) return;
+    const int64_t i = t / nb8, n8 = t - i * nb8, p0 = 8 * n8, e0 = i * P + p0;
+    const int cnt = P - p0 >= 8 ? 8 : (P - p0 > 0 ? (int)(P - p0) : 0);
+    float s[8], v[8];
+    reduce8(partial, splits, n * P, e0, cnt, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        v[j] = (j < cnt && BC[e0 + j] != 0.0f) ? (Y[e0 + j] - s[j] * f1[p0 + j]) * sR[p0 + j] : 0.0f;
+    store_pieces8(B2p, i, n8, Np, v);
 }
 
-// alpha <- soft(alpha + D^T r, T)  (ista.m:21-23) -> alpha (fp32 state) and its pieces
+// alpha <- soft(alpha + D^T r / a, T)  (ista.m:21-23) -> alpha (fp32 state) and its pieces
 __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int splits, int64_t K, int64_t P, int64_t Np,
-                                       int64_t Kp1, float* __restrict__ A, const float* __restrict__ T,
-                                       const float* __restrict__ f2, const float* __restrict__ sA, __half* __restrict__ B1p) {
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= K * P) return;
-    const int64_t k = e / P, p = e - k * P;
-    const float c = reduce_slices(partial, splits, K * P, e) * f2[p];
-    const float x = soft_thr(A[e] + c, T[p]);
-    A[e] = x;
-    __half h1, h2;
-    split_h(x * sA[p], h1, h2);
-    B1p[k * Np + p] = h1;
-    B1p[(Kp1 + k) * Np + p] = h2;
+                                       float* __restrict__ A, const float* __restrict__ T, const float* __restrict__ f2,
+                                       const float* __restrict__ sA, __half* __restrict__ B1p) {
+    const int64_t nb8 = Np / 8, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= K * nb8) return;
+    const int64_t k = t / nb8, n8 = t - k * nb8, p0 = 8 * n8, e0 = k * P + p0;
+    const int cnt = P - p0 >= 8 ? 8 : (P - p0 > 0 ? (int)(P - p0) : 0);
+    float s[8], v[8];
+    reduce8(partial, splits, K * P, e0, cnt, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[j] = 0.f;
+        if (j < cnt) {
+            const float x = soft_thr(A[e0 + j] + s[j] * f2[p0 + j], T[p0 + j]);
+            A[e0 + j] = x;
+            v[j] = x * sA[p0 + j];
+        }
+    }
+    store_pieces8(B1p, k, n8, Np, v);
 }
 
 // Phi_z = D alpha (full dictionary, main_LRS_PnP.py:294)
@@ -279,7 +304,9 @@ __global__ void reduce_store_kernel(const float* __restrict__ partial, int split
                                     const float* __restrict__ f1, float* __restrict__ phi) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n * P) return;
-    phi[e] = reduce_slices(partial, splits, n * P, e) * f1[e % P];
+    float s = partial[e];
+    for (int zz = 1; zz < splits; ++zz) s += partial[(int64_t)zz * n * P + e];
+    phi[e] = s * f1[e % P];
 }
 
 struct Plan {
@@ -390,25 +417,27 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
     const int64_t nD = (int64_t)n * K;
     absmax_kernel<<<(unsigned)((nD + 1023) / 1024 < 592 ? (nD + 1023) / 1024 : 592), 256, 0, st>>>(D, nD, dmax);
     LRS_CHECK_LAUNCH(fn);
-    dict_pieces_kernel<<<(unsigned)((nD + 255) / 256), 256, 0, st>>>(D, n, K, dmax, A1, pl.Mp1, pl.Kp1, A2, pl.Mp2, pl.Kp2);
+    dict_pieces_kernel<<<(unsigned)((nD + 255) / 256), 256, 0, st>>>(D, n, K, dmax, A1, pl.Kp1 / TG_BK, A2, pl.Kp2 / TG_BK);
     LRS_CHECK_LAUNCH(fn);
     column_scales_kernel<<<(unsigned)((P + 63) / 64), 64, 0, st>>>(blocks, n, P, dmax, a, lambda, sA, f1, f2, sR, T);
     LRS_CHECK_LAUNCH(fn);
 
     GemmArgs g1{A1, B1, part, n, P, pl.Mp1, pl.Kp1, pl.Np, pl.kb1, (int)(pl.Kp1 / TG_BK)};   // D alpha
     GemmArgs g2{A2, B2, part, K, P, pl.Mp2, pl.Kp2, pl.Np, pl.kb2, (int)(pl.Kp2 / TG_BK)};   // D^T r
-    const unsigned eb1 = (unsigned)(((int64_t)n * P + 255) / 256), eb2 = (unsigned)(((int64_t)K * P + 255) / 256);
+    const int64_t nb8 = pl.Np / 8;
+    const unsigned eb1 = (unsigned)((n * nb8 + 127) / 128), eb2 = (unsigned)((K * nb8 + 127) / 128);
+    const unsigned es = (unsigned)(((int64_t)n * P + 255) / 256);
     for (int it = 0; it < Nit; ++it) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
-        reduce_residual_kernel<<<eb1, 256, 0, st>>>(part, pl.S1, n, P, pl.Np, pl.Kp2, blocks, blocks_copy, f1, sR, B2);
+        reduce_residual_kernel<<<eb1, 128, 0, st>>>(part, pl.S1, n, P, pl.Np, blocks, blocks_copy, f1, sR, B2);
         LRS_CHECK_LAUNCH(fn);
         if ((rc = tc_gemm(fn, g2, pl.S2, st)) != LRS_OK) return rc;
-        reduce_gradient_kernel<<<eb2, 256, 0, st>>>(part, pl.S2, K, P, pl.Np, pl.Kp1, A, T, f2, sA, B1);
+        reduce_gradient_kernel<<<eb2, 128, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1);
         LRS_CHECK_LAUNCH(fn);
     }
     if (phi) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
-        reduce_store_kernel<<<eb1, 256, 0, st>>>(part, pl.S1, n, P, f1, phi);
+        reduce_store_kernel<<<es, 256, 0, st>>>(part, pl.S1, n, P, f1, phi);
         LRS_CHECK_LAUNCH(fn);
     }
     if (coefs) {
