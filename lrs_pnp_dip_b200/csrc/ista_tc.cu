@@ -233,59 +233,63 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
 }
 
 // ---- reduce kernels: add the split-K slices in a fixed order, apply the epilogue, emit the next operand's pieces ----
-// One thread owns 8 consecutive patches of one row, i.e. one 16-byte chunk of each piece of the B tile image.
-__device__ __forceinline__ void reduce8(const float* __restrict__ partial, int splits, int64_t MN, int64_t e0, int cnt,
-                                        float (&s)[8]) {
-    if (cnt == 8 && ((MN | e0) & 3) == 0) {
-        // aligned full chunk: two 16-byte loads per slice, four slices in flight, slices added in ascending order
+// One thread owns 4 consecutive patches of one row = half a 16-byte chunk of each piece of the B tile image; up to eight
+// slices are in flight per thread (the kernels are latency-bound: 1-2 MB of output against 10 MB of slices).
+// (Measured alternative: reducing inside the GEMM kernel behind a per-row-tile arrival counter, cooperative launch —
+//  23 us per product instead of 9.2 + 6.3 us: the 128 threads of a GEMM CTA cannot hide the L2 latency of its share.)
+__device__ __forceinline__ float4 reduce4(const float* __restrict__ partial, int splits, int64_t MN, int64_t e0, int cnt) {
+    float4 a;
+    if (cnt == 4 && ((MN | e0) & 3) == 0) {
         const float4* q = reinterpret_cast<const float4*>(partial + e0);
         const int64_t st4 = MN / 4;
-        float4 a = q[0], b = q[1];
+        a = q[0];
         int zz = 1;
-        for (; zz + 4 <= splits; zz += 4) {
-            float4 u[4], w[4];
+        for (; zz + 8 <= splits; zz += 8) {
+            float4 u[8];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                u[t] = q[(zz + t) * st4];
-                w[t] = q[(zz + t) * st4 + 1];
-            }
+            for (int t = 0; t < 8; ++t) u[t] = q[(zz + t) * st4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < 8; ++t) {
                 a.x += u[t].x; a.y += u[t].y; a.z += u[t].z; a.w += u[t].w;
-                b.x += w[t].x; b.y += w[t].y; b.z += w[t].z; b.w += w[t].w;
             }
         }
-        for (; zz < splits; ++zz) {
-            const float4 u = q[zz * st4], w = q[zz * st4 + 1];
-            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
-            b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
-        }
-        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
-        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-        return;
-    }
+        float4 u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = j < cnt ? partial[e0 + j] : 0.f;
+        for (int t = 0; t < 8; ++t)
+            if (zz + t < splits) u[t] = q[(zz + t) * st4];
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (zz + t < splits) {
+                a.x += u[t].x; a.y += u[t].y; a.z += u[t].z; a.w += u[t].w;
+            }
+        return a;
+    }
+    float s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = j < cnt ? partial[e0 + j] : 0.f;
     for (int zz = 1; zz < splits; ++zz) {
         const float* q = partial + (int64_t)zz * MN + e0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 4; ++j)
             if (j < cnt) s[j] += q[j];
     }
+    return make_float4(s[0], s[1], s[2], s[3]);
 }
-__device__ __forceinline__ void store_pieces8(__half* __restrict__ Bp, int64_t row, int64_t n8, int64_t Np, const float (&v)[8]) {
-    uint32_t w1[4], w2[4];
+// patches 4*n4 .. 4*n4+3 of row `row` -> 8 bytes of each piece
+__device__ __forceinline__ void store_pieces4(__half* __restrict__ Bp, int64_t row, int64_t n4, int64_t Np, const float (&v)[4]) {
+    uint32_t w1[2], w2[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
         __half a1, a2, b1, b2;
         split_h(v[2 * j], a1, a2);
         split_h(v[2 * j + 1], b1, b2);
         w1[j] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
         w2[j] = (uint32_t)__half_as_ushort(a2) | ((uint32_t)__half_as_ushort(b2) << 16);
     }
-    __half* t = Bp + (row >> 6) * (2 * Np * 64) + n8 * 512 + (row & 63) * 8;   // k block, patch group, k within the block
-    *reinterpret_cast<uint4*>(t) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-    *reinterpret_cast<uint4*>(t + Np * 64) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+    // k block, patch group of 8, k within the block, half of the 16-byte chunk
+    __half* t = Bp + (row >> 6) * (2 * Np * 64) + (n4 >> 1) * 512 + (row & 63) * 8 + (n4 & 1) * 4;
+    *reinterpret_cast<uint2*>(t) = make_uint2(w1[0], w1[1]);
+    *reinterpret_cast<uint2*>(t + Np * 64) = make_uint2(w2[0], w2[1]);
 }
 
 // r = m .* (y - D alpha)  -> r pieces (the division by the step constant happens after D^T r, in f2)
@@ -293,30 +297,32 @@ __global__ void reduce_residual_kernel(const float* __restrict__ partial, int sp
                                        const float* __restrict__ Y, const float* __restrict__ BC,
                                        const float* __restrict__ f1, const float* __restrict__ sR,
                                        __half* __restrict__ B2p) {
-    const int64_t nb8 = Np / 8, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n * nb8) return;
-    const int64_t i = t / nb8, n8 = t - i * nb8, p0 = 8 * n8, e0 = i * P + p0;
-    const int cnt = P - p0 >= 8 ? 8 : (P - p0 > 0 ? (int)(P - p0) : 0);
-    float s[8], v[8];
-    reduce8(partial, splits, n * P, e0, cnt, s);
+    const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * nb4) return;
+    const int64_t i = t / nb4, n4 = t - i * nb4, p0 = 4 * n4, e0 = i * P + p0;
+    const int cnt = P - p0 >= 4 ? 4 : (P - p0 > 0 ? (int)(P - p0) : 0);
+    const float4 s4 = reduce4(partial, splits, n * P, e0, cnt);
+    const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+    float v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
         v[j] = (j < cnt && BC[e0 + j] != 0.0f) ? (Y[e0 + j] - s[j] * f1[p0 + j]) * sR[p0 + j] : 0.0f;
-    store_pieces8(B2p, i, n8, Np, v);
+    store_pieces4(B2p, i, n4, Np, v);
 }
 
 // alpha <- soft(alpha + D^T r / a, T)  (ista.m:21-23) -> alpha (fp32 state) and its pieces
 __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int splits, int64_t K, int64_t P, int64_t Np,
                                        float* __restrict__ A, const float* __restrict__ T, const float* __restrict__ f2,
                                        const float* __restrict__ sA, __half* __restrict__ B1p) {
-    const int64_t nb8 = Np / 8, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= K * nb8) return;
-    const int64_t k = t / nb8, n8 = t - k * nb8, p0 = 8 * n8, e0 = k * P + p0;
-    const int cnt = P - p0 >= 8 ? 8 : (P - p0 > 0 ? (int)(P - p0) : 0);
-    float s[8], v[8];
-    reduce8(partial, splits, K * P, e0, cnt, s);
+    const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= K * nb4) return;
+    const int64_t k = t / nb4, n4 = t - k * nb4, p0 = 4 * n4, e0 = k * P + p0;
+    const int cnt = P - p0 >= 4 ? 4 : (P - p0 > 0 ? (int)(P - p0) : 0);
+    const float4 s4 = reduce4(partial, splits, K * P, e0, cnt);
+    const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+    float v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
         v[j] = 0.f;
         if (j < cnt) {
             const float x = soft_thr(A[e0 + j] + s[j] * f2[p0 + j], T[p0 + j]);
@@ -324,7 +330,7 @@ __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int sp
             v[j] = x * sA[p0 + j];
         }
     }
-    store_pieces8(B1p, k, n8, Np, v);
+    store_pieces4(B1p, k, n4, Np, v);
 }
 
 // Phi_z = D alpha (full dictionary, main_LRS_PnP.py:294)
@@ -452,8 +458,8 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
 
     GemmArgs g1{A1, B1, part, n, P, pl.Mp1, pl.Kp1, pl.Np, pl.kb1, (int)(pl.Kp1 / TG_BK)};   // D alpha
     GemmArgs g2{A2, B2, part, K, P, pl.Mp2, pl.Kp2, pl.Np, pl.kb2, (int)(pl.Kp2 / TG_BK)};   // D^T r
-    const int64_t nb8 = pl.Np / 8;
-    const unsigned eb1 = (unsigned)((n * nb8 + 63) / 64), eb2 = (unsigned)((K * nb8 + 63) / 64);
+    const int64_t nb4 = pl.Np / 4;
+    const unsigned eb1 = (unsigned)((n * nb4 + 63) / 64), eb2 = (unsigned)((K * nb4 + 63) / 64);
     const unsigned es = (unsigned)(((int64_t)n * P + 255) / 256);
     for (int it = 0; it < Nit; ++it) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
