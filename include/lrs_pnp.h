@@ -110,7 +110,11 @@ int lrs_spectral_table_f32(const float* D_dev, int K, int bb, int step, float* t
  * with m = (blocks_copy[:,p] != 0)  [row deletion of main_LRS_PnP.py:276-289 in masked form],
  * then phi_z[:,p] = D alpha (full dictionary, :294/:302).  Patches with a_p <= 0 give alpha = 0.
  * Replaces the jj loop main_LRS_PnP.py:270-303 + ista :131-149 / ista.m:13-24.
- * coefs_dev [K,P] and phi_z_dev [n,P] may each be NULL.  Any n, K, P. */
+ * coefs_dev [K,P] and phi_z_dev [n,P] may each be NULL.  Any n, K, P.
+ * Engines (chosen per call, same results to <= 2e-5 relative): for 8 <= P <= 256 and n, K >= 128 (the 36x36-patch
+ * configurations) the two products of an iteration run as split-K tcgen05 GEMMs with a 3-pass fp16 operand split
+ * (ista_tc.cu); every other shape, and the environment override LRS_ISTA_ENGINE=simt, uses the fp32 FFMA kernels.
+ * lrs_ista_workspace_bytes covers whichever engine the shape may take. */
 size_t lrs_ista_workspace_bytes(int n, int K, int64_t P);
 int lrs_ista_soft_f32(const float* blocks_dev, const float* blocks_copy_dev, const float* D_dev, const float* a_dev,
                       float lambda_ista, int Nit, int n, int K, int64_t P, float* coefs_dev, float* phi_z_dev,
