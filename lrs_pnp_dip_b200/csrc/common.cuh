@@ -124,7 +124,10 @@ bool ista_tc_shape_ok(int n, int K, int64_t P);
 bool ista_tc_enabled();
 size_t ista_tc_workspace_bytes(int n, int K, int64_t P);
 int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, const float* a, float lambda, int Nit, int n,
-                int K, int64_t P, float* coefs, float* phi, void* ws, size_t ws_bytes, cudaStream_t st);
+                int K, int64_t P, int denoiser, float h_scale, float* coefs, float* phi, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+// ista_generic.cu: A = NLmeansfilter(G, 3, 3, h_scale * T) column by column (NLmeansfilter.m:18-91)
+int nlm_columns(const char* fn, const float* G, const float* T, float h_scale, int K, int64_t P, float* A, cudaStream_t st);
 
 int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st);  // sparse_fused_tc.cu
 bool sparse_fused_tc_supported(const FusedParams& prm, int K);

@@ -352,6 +352,14 @@ int svt_apply_impl(const float* X, const float* L, float c, const float* W, int6
     return LRS_OK;
 }
 
+int nlm_columns(const char* fn, const float* G, const float* T, float h_scale, int K, int64_t P, float* A, cudaStream_t st) {
+    if (K > 65535) return fail_arg(fn, "K too large for the NLM denoiser");
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)K);
+    nlm_column_kernel<<<grid, 128, 0, st>>>(G, T, h_scale, K, P, A);
+    note_launch();
+    return check_cuda(fn, cudaGetLastError());
+}
+
 }  // namespace lrs
 
 using namespace lrs;
@@ -390,9 +398,9 @@ int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, cons
         return LRS_E_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (denoiser == LRS_DENOISE_SOFT && ista_tc_shape_ok(n, K, P) && ista_tc_enabled())
-        return ista_tc_run(blocks_dev, blocks_copy_dev, D_dev, a_dev, lambda_ista, Nit, n, K, P, coefs_dev, phi_z_dev,
-                           workspace_dev, workspace_bytes, st);
+    if (ista_tc_shape_ok(n, K, P) && ista_tc_enabled())
+        return ista_tc_run(blocks_dev, blocks_copy_dev, D_dev, a_dev, lambda_ista, Nit, n, K, P, denoiser, h_scale, coefs_dev,
+                           phi_z_dev, workspace_dev, workspace_bytes, st);
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
     char* w = (char*)workspace_dev;
     float* A = (float*)w;
@@ -421,11 +429,7 @@ int lrs_ista_pnp_f32(const float* blocks_dev, const float* blocks_copy_dev, cons
         } else {
             rc = launch_gemm<true>(fn, LoadPlain{D_dev}, Rm, K, P, n, EpiGradientPlain{A, Gd}, st, scratch);
             if (rc != LRS_OK) return rc;
-            dim3 grid((unsigned)((P + 127) / 128), (unsigned)K);
-            if (K > 65535) return fail_arg(fn, "K too large for the NLM denoiser");
-            nlm_column_kernel<<<grid, 128, 0, st>>>(Gd, T, h_scale, K, P, A);
-            note_launch();
-            rc = check_cuda(fn, cudaGetLastError());
+            rc = nlm_columns(fn, Gd, T, h_scale, K, P, A, st);
         }
         if (rc != LRS_OK) return rc;
     }

@@ -310,10 +310,13 @@ __global__ void reduce_residual_kernel(const float* __restrict__ partial, int sp
     store_pieces4(B2p, i, n4, Np, v);
 }
 
-// alpha <- soft(alpha + D^T r / a, T)  (ista.m:21-23) -> alpha (fp32 state) and its pieces
+// g = alpha + D^T r / a ;  GRAD_SOFT: alpha <- soft(g, T) (ista.m:21-23) ; GRAD_IDENTITY: alpha <- g ; both emit the
+// pieces of the new alpha.  GRAD_PLAIN: G <- g for a plug-and-play denoiser that runs as its own kernel (pnp_ista.m:30).
+enum { GRAD_SOFT = 0, GRAD_IDENTITY = 1, GRAD_PLAIN = 2 };
+template <int MODE>
 __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int splits, int64_t K, int64_t P, int64_t Np,
                                        float* __restrict__ A, const float* __restrict__ T, const float* __restrict__ f2,
-                                       const float* __restrict__ sA, __half* __restrict__ B1p) {
+                                       const float* __restrict__ sA, __half* __restrict__ B1p, float* __restrict__ G) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= K * nb4) return;
     const int64_t k = t / nb4, n4 = t - k * nb4, p0 = 4 * n4, e0 = k * P + p0;
@@ -325,11 +328,28 @@ __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int sp
     for (int j = 0; j < 4; ++j) {
         v[j] = 0.f;
         if (j < cnt) {
-            const float x = soft_thr(A[e0 + j] + s[j] * f2[p0 + j], T[p0 + j]);
-            A[e0 + j] = x;
-            v[j] = x * sA[p0 + j];
+            const float g = A[e0 + j] + s[j] * f2[p0 + j];
+            if (MODE == GRAD_PLAIN) {
+                G[e0 + j] = g;
+            } else {
+                const float x = MODE == GRAD_SOFT ? soft_thr(g, T[p0 + j]) : g;
+                A[e0 + j] = x;
+                v[j] = x * sA[p0 + j];
+            }
         }
     }
+    if (MODE != GRAD_PLAIN) store_pieces4(B1p, k, n4, Np, v);
+}
+
+// pieces of a coefficient matrix that another kernel produced (the NLM denoiser)
+__global__ void alpha_pieces_kernel(const float* __restrict__ A, int64_t K, int64_t P, int64_t Np, const float* __restrict__ sA,
+                                    __half* __restrict__ B1p) {
+    const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= K * nb4) return;
+    const int64_t k = t / nb4, n4 = t - k * nb4, p0 = 4 * n4, e0 = k * P + p0;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = p0 + j < P ? A[e0 + j] * sA[p0 + j] : 0.f;
     store_pieces4(B1p, k, n4, Np, v);
 }
 
@@ -346,7 +366,7 @@ __global__ void reduce_store_kernel(const float* __restrict__ partial, int split
 struct Plan {
     int64_t Mp1, Kp1, Mp2, Kp2, Np;
     int S1, kb1, S2, kb2;   // splits and k blocks per split of both products
-    size_t off_A, off_vec, off_dmax, off_A1, off_A2, off_B1, off_B2, off_part, total;
+    size_t off_A, off_vec, off_dmax, off_A1, off_A2, off_B1, off_B2, off_part, off_G, total;
 };
 
 size_t al256(size_t b) { return (b + 255) / 256 * 256; }
@@ -387,6 +407,8 @@ Plan make_plan(int n, int K, int64_t P, int sms) {
     pl.off_part = o;
     const size_t p1 = (size_t)pl.S1 * n * P * 4, p2 = (size_t)pl.S2 * K * P * 4;
     o += al256(p1 > p2 ? p1 : p2);
+    pl.off_G = o;                          // input of a plug-and-play denoiser
+    o += al256((size_t)K * P * 4);
     pl.total = o;
     return pl;
 }
@@ -426,7 +448,8 @@ static int tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t s
 }
 
 int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, const float* a, float lambda, int Nit,
-                int n, int K, int64_t P, float* coefs, float* phi, void* ws, size_t ws_bytes, cudaStream_t st) {
+                int n, int K, int64_t P, int denoiser, float h_scale, float* coefs, float* phi, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
     const char* fn = "lrs_ista_pnp_f32";
     const Plan pl = make_plan(n, K, P, PLAN_SMS);
     if (ws_bytes < pl.total) {
@@ -444,6 +467,7 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
     __half* B1 = (__half*)(w + pl.off_B1);
     __half* B2 = (__half*)(w + pl.off_B2);
     float* part = (float*)(w + pl.off_part);
+    float* Gd = (float*)(w + pl.off_G);
 
     // x0 = 0 (ista.m:14), zero padding of every piece buffer, max |D|
     int rc = check_cuda(fn, cudaMemsetAsync(w + pl.off_A, 0, pl.off_part - pl.off_A, st));
@@ -466,8 +490,19 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
         reduce_residual_kernel<<<eb1, 64, 0, st>>>(part, pl.S1, n, P, pl.Np, blocks, blocks_copy, f1, sR, B2);
         LRS_CHECK_LAUNCH(fn);
         if ((rc = tc_gemm(fn, g2, pl.S2, st)) != LRS_OK) return rc;
-        reduce_gradient_kernel<<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1);
-        LRS_CHECK_LAUNCH(fn);
+        if (denoiser == LRS_DENOISE_SOFT) {
+            reduce_gradient_kernel<GRAD_SOFT><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, nullptr);
+            LRS_CHECK_LAUNCH(fn);
+        } else if (denoiser == LRS_DENOISE_IDENTITY) {
+            reduce_gradient_kernel<GRAD_IDENTITY><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, nullptr);
+            LRS_CHECK_LAUNCH(fn);
+        } else {
+            reduce_gradient_kernel<GRAD_PLAIN><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, Gd);
+            LRS_CHECK_LAUNCH(fn);
+            if ((rc = nlm_columns(fn, Gd, T, h_scale, K, P, A, st)) != LRS_OK) return rc;
+            alpha_pieces_kernel<<<eb2, 64, 0, st>>>(A, K, P, pl.Np, sA, B1);
+            LRS_CHECK_LAUNCH(fn);
+        }
     }
     if (phi) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
