@@ -48,6 +48,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  : "memory");
 }
 
+// Programmatic dependent launch: the 2*Nit+1 GEMM / reduce launches of a call form a chain in one stream.  Every kernel
+// lets its successor start launching at once (its CTAs become resident as resources free up and run their set-up) and
+// waits for its predecessor's results right before it first touches them.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // max |x| as float bits (non-negative floats order like their bit patterns)
 __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
     float m = 0.f;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     __shared__ uint64_t bar_done;
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_launch_dependents();
     const uint32_t b_piece = (uint32_t)g.Np * 128u, a_bytes = 2 * A_PIECE, b_bytes = 2 * b_piece, stage_bytes = a_bytes + b_bytes;
     const int64_t m0 = blockIdx.x * (int64_t)TG_BM;
     const int z = blockIdx.y;
@@ -160,6 +167,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     tc_fence_after();
     const uint32_t tbase = tmem_base_slot;
     const uint32_t sbase = smem_u32(smem);
+    pdl_wait();   // the B pieces come from the previous reduce kernel, which also still reads `partial`
 
     if (warp == 1 && lane == 0) {
         // ---- producer: one 32 KB bulk copy for the A stage, one for the B stage ----
@@ -298,6 +306,8 @@ __global__ void reduce_residual_kernel(const float* __restrict__ partial, int sp
                                        const float* __restrict__ f1, const float* __restrict__ sR,
                                        __half* __restrict__ B2p) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (t >= n * nb4) return;
     const int64_t i = t / nb4, n4 = t - i * nb4, p0 = 4 * n4, e0 = i * P + p0;
     const int cnt = P - p0 >= 4 ? 4 : (P - p0 > 0 ? (int)(P - p0) : 0);
@@ -318,6 +328,8 @@ __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int sp
                                        float* __restrict__ A, const float* __restrict__ T, const float* __restrict__ f2,
                                        const float* __restrict__ sA, __half* __restrict__ B1p, float* __restrict__ G) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (t >= K * nb4) return;
     const int64_t k = t / nb4, n4 = t - k * nb4, p0 = 4 * n4, e0 = k * P + p0;
     const int cnt = P - p0 >= 4 ? 4 : (P - p0 > 0 ? (int)(P - p0) : 0);
@@ -431,15 +443,32 @@ bool ista_tc_enabled() {
     return major == 10;
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <class... KArgs, class... Args>
+static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool plain = getenv("LRS_ISTA_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = plain ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int STAGES>
 static int launch_tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
     const size_t smem = (size_t)STAGES * (2 * A_PIECE + 2 * (size_t)g.Np * 128);
     int rc = check_cuda(fn, cudaFuncSetAttribute(tc_gemm_splitk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
     dim3 grid((unsigned)(g.Mp / TG_BM), (unsigned)splits);
-    tc_gemm_splitk_kernel<STAGES><<<grid, TG_THREADS, smem, st>>>(g);
+    rc = check_cuda(fn, launch_chained(tc_gemm_splitk_kernel<STAGES>, grid, dim3(TG_THREADS), smem, st, g));
     note_launch();
-    return check_cuda(fn, cudaGetLastError());
+    return rc;
 }
 
 static int tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
@@ -487,18 +516,28 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
     const unsigned es = (unsigned)(((int64_t)n * P + 255) / 256);
     for (int it = 0; it < Nit; ++it) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
-        reduce_residual_kernel<<<eb1, 64, 0, st>>>(part, pl.S1, n, P, pl.Np, blocks, blocks_copy, f1, sR, B2);
-        LRS_CHECK_LAUNCH(fn);
+        rc = check_cuda(fn, launch_chained(reduce_residual_kernel, dim3(eb1), dim3(64), 0, st, (const float*)part, pl.S1, (int64_t)n, P,
+                                           pl.Np, blocks, blocks_copy, (const float*)f1, (const float*)sR, B2));
+        note_launch();
+        if (rc != LRS_OK) return rc;
         if ((rc = tc_gemm(fn, g2, pl.S2, st)) != LRS_OK) return rc;
         if (denoiser == LRS_DENOISE_SOFT) {
-            reduce_gradient_kernel<GRAD_SOFT><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, nullptr);
-            LRS_CHECK_LAUNCH(fn);
+            rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_SOFT>, dim3(eb2), dim3(64), 0, st, (const float*)part, pl.S2,
+                                               (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1,
+                                               (float*)nullptr));
+            note_launch();
+            if (rc != LRS_OK) return rc;
         } else if (denoiser == LRS_DENOISE_IDENTITY) {
-            reduce_gradient_kernel<GRAD_IDENTITY><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, nullptr);
-            LRS_CHECK_LAUNCH(fn);
+            rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_IDENTITY>, dim3(eb2), dim3(64), 0, st, (const float*)part,
+                                               pl.S2, (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1,
+                                               (float*)nullptr));
+            note_launch();
+            if (rc != LRS_OK) return rc;
         } else {
-            reduce_gradient_kernel<GRAD_PLAIN><<<eb2, 64, 0, st>>>(part, pl.S2, K, P, pl.Np, A, T, f2, sA, B1, Gd);
-            LRS_CHECK_LAUNCH(fn);
+            rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_PLAIN>, dim3(eb2), dim3(64), 0, st, (const float*)part, pl.S2,
+                                               (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1, Gd));
+            note_launch();
+            if (rc != LRS_OK) return rc;
             if ((rc = nlm_columns(fn, Gd, T, h_scale, K, P, A, st)) != LRS_OK) return rc;
             alpha_pieces_kernel<<<eb2, 64, 0, st>>>(A, K, P, pl.Np, sA, B1);
             LRS_CHECK_LAUNCH(fn);
