@@ -95,12 +95,18 @@ constexpr uint32_t A2_SMEM_BYTES = (A2_SS ? 64 * 1024 : 0) + (A1_SS ? 64 * 1024 
 constexpr uint32_t A1_OFF = 64 * 1024;   // a1 pieces follow the a2 pieces, same layout
 constexpr uint32_t A2_SK = 2048, A2_SM = 128;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
+// Next tile's patch values, gathered by the otherwise idle warps 1..3 while the current tile iterates:
+// V = X + L/mu as [pixel][patch] floats (32 KB) and the observed flags as [pixel][patch] bytes (8 KB)
+constexpr uint32_t G_SMEM_BYTES = 64 * TILE * 4 + 64 * TILE;
+constexpr int NLOAD = 32 * (FIRST_EPI - 1);   // loader threads
 
 struct __align__(8) Shared {
     uint64_t bar_R[4];        // epilogue -> MMA: residual pieces of pixel quarter ks are in shared memory (NEPI warps)
     uint64_t bar_B[2];        // MMA -> epilogue: GEMM-B complete for atom half h (h = 0 only when !B_SS)      (commit)
     uint64_t bar_S[MAXCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
     uint64_t bar_A[MAXCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
+    uint64_t bar_G_full;      // loader -> epilogue: the gathered values of the next tile are in shared memory (loader warps)
+    uint64_t bar_G_free;      // epilogue -> loader: the gather buffer has been consumed                      (NEPI warps)
     uint32_t tmem_base;
     float xmax[NCG][TILE];    // per-patch partial max |y| of the pixel groups
     float xsum[NCG][TILE];    // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
@@ -213,6 +219,31 @@ struct TileWalk {
     }
 };
 
+// Lane m of the current tile: its patch (clamped to some patch of the range when the lane is idle, so that it computes
+// finite garbage and stores nothing), the window origin and the Phi_z column.
+struct PatchRef {
+    int64_t p, pi, rs, cs;
+    bool valid;
+};
+__device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, const TileWalk& tw, int m) {
+    const int64_t nR = prm.g.row.n;
+    int64_t ci = tw.ci, ri = (int64_t)tw.rb * TILE + m;
+    int64_t p = ci * nR + ri;
+    PatchRef r;
+    r.valid = ri < nR && p >= prm.p_begin && p < prm.p_end;
+    r.pi = p - prm.p_begin;
+    if (!r.valid) {
+        p = p < prm.p_begin ? prm.p_begin : prm.p_end - 1;
+        if (ri >= nR && tw.ci * nR + nR - 1 >= prm.p_begin && tw.ci * nR + nR - 1 < prm.p_end) p = tw.ci * nR + nR - 1;
+        ci = p / nR;
+        ri = p - ci * nR;
+    }
+    r.p = p;
+    r.rs = prm.g.row.start(ri);
+    r.cs = prm.g.col.start(ci);
+    return r;
+}
+
 // KATOMS in {128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
 template <bool DBG, int KATOMS>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm, TilePlan plan) {
@@ -224,7 +255,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     uint8_t* Dsm = smem;
     uint8_t* Rsm = smem + D_SMEM_BYTES;
     uint8_t* A2sm = smem + D_SMEM_BYTES + R_SMEM_BYTES;
-    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES);
+    float* Gv = reinterpret_cast<float*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES);
+    uint8_t* Gok = smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + 64 * TILE * 4;
+    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = prm.p_end - prm.p_begin;
@@ -273,6 +306,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             mbar_init(&sh.bar_S[j], NEPI);
             mbar_init(&sh.bar_A[j], 1);
         }
+        mbar_init(&sh.bar_G_full, FIRST_EPI - 1);
+        mbar_init(&sh.bar_G_free, NEPI);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(&sh.tmem_base, 512);
@@ -369,8 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         const int cg = (warp - FIRST_EPI) >> 2;     // column group: CW of every 64 columns, pixels [CW*cg, CW*cg+CW)
         const int m = q * 32 + lane;                // patch within the tile = TMEM lane
         const uint32_t lane_addr = tbase + ((uint32_t)(q * 32) << 16);
-        const int64_t nR = prm.g.row.n, C = prm.g.C;
-        uint32_t gi = 0;
+        uint32_t gi = 0, tcount = 0;
         long long ed[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long e_begin = TSTAMP();
         for (TileWalk tw; tw.next(plan, prm);) {
@@ -378,26 +412,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             // ---- tile prologue: gather my CW pixels, mask, step constant, scale.  Register slot c holds pixel
             //      16*(c/8) + 8*cg + c%8 = window row c%8, column 2*(c/8) + cg: every 16-pixel GEMM-B k-step is shared by
             //      the two column groups, so that all warps finish quarter ks together and its MMAs start early ----
-            int64_t ci = tw.ci, ri = (int64_t)tw.rb * TILE + m;
-            int64_t p = ci * nR + ri;
-            const bool valid = ri < nR && p >= prm.p_begin && p < prm.p_end;
-            const int64_t pi = p - prm.p_begin;                 // Phi_z column
-            if (!valid) {                                       // idle lane: recompute some patch of the range, store nothing
-                p = p < prm.p_begin ? prm.p_begin : prm.p_end - 1;
-                if (ri >= nR && tw.ci * nR + nR - 1 >= prm.p_begin && tw.ci * nR + nR - 1 < prm.p_end) p = tw.ci * nR + nR - 1;
-                ci = p / nR;
-                ri = p - ci * nR;
-            }
-            const int64_t rs = prm.g.row.start(ri), cs = prm.g.col.start(ci);
+            const PatchRef pr = tile_patch(prm, tw, m);
+            const bool valid = pr.valid;
+            const int64_t pi = pr.pi, p = pr.p;                 // Phi_z column; patch for the step constant
             float ysc[CW];
             uint32_t mbits = 0;
             float amax = 0.f, nsum = 0.f;
+            mbar_wait(&sh.bar_G_full, tcount & 1);              // gathered by warps 1..3 during the previous tile
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
-                const int64_t src = (rs + (c & 7)) * C + cs + NCG * (c >> 3) + cg;
-                float v = __ldg(prm.X + src);
-                if (prm.L) v = __fadd_rn(v, __fdiv_rn(__ldg(prm.L + src), prm.mu1));
-                const bool ok = __ldg(prm.Yobs + src) != 0.0f;
+                const int pix = 16 * (c >> 3) + NPX * cg + (c & 7);
+                const float v = Gv[pix * TILE + m];
+                const bool ok = Gok[pix * TILE + m] != 0;
                 ysc[c] = v;
                 if (ok) {
                     mbits |= 1u << c;
@@ -405,6 +431,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     nsum += sh.rn[16 * (c >> 3) + NPX * cg + (c & 7)];
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.bar_G_free);         // the loader may fetch the next tile
+            ++tcount;
             sh.xmax[cg][m] = amax;
             sh.xsum[cg][m] = nsum;
             if (cg == 0) sh.xrow[m] = mbits & 0xFFu;
@@ -574,6 +603,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             g_tc_timing[16] = clock64() - e_begin;
             for (int i = 1; i < 9; ++i) g_tc_timing[16 + i] = ed[i];
         }
+    } else {
+        // ================================ gather warps (1 .. FIRST_EPI-1) ================================
+        // One tile ahead of the epilogue: V = X + L/mu and the observed flags of the next tile's 128 x 64 window values
+        // go to shared memory while the current tile iterates, so the tile prologue no longer waits on global memory.
+        const int lt = tid - 32;
+        const int64_t C = prm.g.C;
+        uint32_t t = 0;
+        for (TileWalk tw; tw.next(plan, prm); ++t) {
+            if (t > 0) mbar_wait(&sh.bar_G_free, (t - 1) & 1);
+            for (int m = lt; m < TILE; m += NLOAD) {
+                const PatchRef pr = tile_patch(prm, tw, m);
+                const float* xs = prm.X + pr.rs * C + pr.cs;
+                const float* ys = prm.Yobs + pr.rs * C + pr.cs;
+                const float* ls = prm.L ? prm.L + pr.rs * C + pr.cs : nullptr;
+#pragma unroll 2
+                for (int j = 0; j < 8; ++j) {            // window column j: pixels 8j .. 8j+7 = rows 0..7
+                    float v[8], o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i] = __ldg(xs + i * C + j);
+                        o[i] = __ldg(ys + i * C + j);
+                    }
+                    if (ls) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __fadd_rn(v[i], __fdiv_rn(__ldg(ls + i * C + j), prm.mu1));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        Gv[(8 * j + i) * TILE + m] = v[i];
+                        Gok[(8 * j + i) * TILE + m] = o[i] != 0.0f ? 1 : 0;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.bar_G_full);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -593,7 +658,7 @@ bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
 template <int K>
 static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
-    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + sizeof(Shared);
+    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
     auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
