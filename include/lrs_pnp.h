@@ -51,7 +51,7 @@ extern "C" {
 /* engines of lrs_sparse_step_fused_f32 */
 #define LRS_ENGINE_AUTO 0
 #define LRS_ENGINE_SIMT 1   /* fp32 FFMA kernel (any K multiple of 16 up to 256)          */
-#define LRS_ENGINE_TC 2     /* tcgen05/TMEM kernel, 3-pass fp16 split (n = 64, K in {128,192,256}) */
+#define LRS_ENGINE_TC 2     /* tcgen05/TMEM kernel, 3-pass fp16 split (n = 64, K in {64,128,192,256}) */
 
 typedef void* lrs_stream_t;
 

@@ -210,7 +210,7 @@ extern "C" int lrs_sparse_step_fused_f32(const float* X_dev, const float* L_dev,
     cudaStream_t st = (cudaStream_t)stream;
     if (engine == LRS_ENGINE_TC || (engine == LRS_ENGINE_AUTO && sparse_fused_tc_supported(prm, K))) {
         if (!sparse_fused_tc_supported(prm, K))
-            return fail_arg(fn, "tcgen05 engine needs K in {128,192,256}, Nit >= 1 and an sm_100 device");
+            return fail_arg(fn, "tcgen05 engine needs K in {64,128,192,256}, Nit >= 1 and an sm_100 device");
         return sparse_fused_tc_launch(prm, K, st);
     }
     if (engine != LRS_ENGINE_SIMT && engine != LRS_ENGINE_AUTO) return fail_arg(fn, "unknown engine");

@@ -244,13 +244,13 @@ __device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, const Til
     return r;
 }
 
-// KATOMS in {128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
+// KATOMS in {64, 128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
 template <bool DBG, int KATOMS>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm, TilePlan plan) {
     constexpr int NCHUNK = KATOMS / 64;
     constexpr int KH = KATOMS / 2;                    // atoms per GEMM-B half (MMA N)
     constexpr int FIRST_B1_CHUNK = (KH + 63) / 64 - ((KH % 64) ? 1 : 0);   // first chunk touching the second half
-    static_assert(KATOMS % 64 == 0 && KATOMS >= 128 && KATOMS <= 256 && KH % 16 == 0, "unsupported K");
+    static_assert(KATOMS % 64 == 0 && KATOMS >= 64 && KATOMS <= 256 && KH % 16 == 0, "unsupported K");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
     uint8_t* Rsm = smem + D_SMEM_BYTES;
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 }  // namespace
 
 bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
-    if ((K != 128 && K != 192 && K != 256) || prm.g.bb != 8 || prm.Nit < 1) return false;
+    if ((K != 64 && K != 128 && K != 192 && K != 256) || prm.g.bb != 8 || prm.Nit < 1) return false;
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
@@ -685,8 +685,9 @@ static int launch_tc(const FusedParams& prm, cudaStream_t st) {
 
 int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     if (!sparse_fused_tc_supported(prm, K))
-        return fail_arg("lrs_sparse_step_fused_f32", "tcgen05 engine needs K in {128,192,256}, Nit >= 1 and an sm_100 device");
+        return fail_arg("lrs_sparse_step_fused_f32", "tcgen05 engine needs K in {64,128,192,256}, Nit >= 1 and an sm_100 device");
     switch (K) {
+        case 64: return launch_tc<64>(prm, st);
         case 128: return launch_tc<128>(prm, st);
         case 192: return launch_tc<192>(prm, st);
         default: return launch_tc<256>(prm, st);
