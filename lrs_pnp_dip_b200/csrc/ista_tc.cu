@@ -31,7 +31,10 @@ constexpr float TS_D = 4.0f;       // D pieces  = fp16(4 sd D)
 constexpr float TS_R = 0.25f;      // r pieces  = fp16(r' / 4)     (TS_D * TS_R = 1)
 constexpr uint32_t A_PIECE = TG_BM * TG_BK * 2;     // 16 KB: [8 k-groups][128 rows][8 halves]
 
+constexpr int TG_BN = 256;         // patches per tile of the B operand (MMA N)
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int64_t ptile_width(int64_t Np, int64_t t) { return Np - t * TG_BN < TG_BN ? Np - t * TG_BN : TG_BN; }
+__host__ __device__ inline int64_t b_slot_halves(int64_t Np) { return 2 * (Np < TG_BN ? Np : TG_BN) * 64; }
 
 __device__ __forceinline__ void split_h(float x, __half& h1, __half& h2) {
     h1 = __float2half_rn(x);
@@ -73,7 +76,9 @@ __device__ __forceinline__ float pow2_down_scale(const unsigned* dmax_bits) {   
 // Operand pieces live in global memory as the exact images of the shared-memory stages, so that a stage is ONE
 // contiguous bulk copy:
 //   A tile (128 rows x 64 k), 32 KB:  halves  [piece][k/8][row][k%8]                 tile index = mtile * (Kp/64) + kblock
-//   B tile (64 k x Np patches):       halves  [piece][p/8][k][p%8]                   tile index = kblock
+//   B tile (64 k x w patches):        halves  [piece][p/8][k][p%8]                   tile index = ptile * (Kp/64) + kblock
+// The patch axis is cut into tiles of TG_BN = 256 columns (one MMA N, one TMEM accumulator); w is 256 except for the
+// last tile.  Every B tile occupies a slot of 2 * min(Np, 256) * 64 halves.
 __device__ __forceinline__ int64_t a_tile_offset(int64_t row, int64_t k, int64_t nkb) {
     return (((row >> 7) * nkb + (k >> 6)) << 14) + (((k & 63) >> 3) << 10) + ((row & 127) << 3) + (k & 7);
 }
@@ -127,7 +132,7 @@ struct GemmArgs {
     const __half* Bp;    // B tiles, Kp/64 of them
     float* partial;      // [splits][M][N]
     int64_t M, N;        // logical output size
-    int64_t Mp, Kp, Np;  // padded sizes (Mp % 128 == 0, Kp % 64 == 0, Np % 16 == 0, Np <= 256)
+    int64_t Mp, Kp, Np;  // padded sizes (Mp % 128 == 0, Kp % 64 == 0, Np % 16 == 0)
     int kb_per_split;    // 64-wide k blocks per split
     int nkb_total;       // Kp / 64
 };
@@ -147,7 +152,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     pdl_launch_dependents();
-    const uint32_t b_piece = (uint32_t)g.Np * 128u, a_bytes = 2 * A_PIECE, b_bytes = 2 * b_piece, stage_bytes = a_bytes + b_bytes;
+    const int pt = blockIdx.z;                                       // patch tile
+    const uint32_t w = (uint32_t)ptile_width(g.Np, pt);              // its width (columns of the accumulator)
+    const uint32_t b_piece = w * 128u, a_bytes = 2 * A_PIECE, b_bytes = 2 * b_piece;
+    const uint32_t stage_bytes = a_bytes + (uint32_t)b_slot_halves(g.Np) * 2u;   // stage stride (widest tile)
     const int64_t m0 = blockIdx.x * (int64_t)TG_BM;
     const int z = blockIdx.y;
     const int kb0 = z * g.kb_per_split;
@@ -172,19 +180,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     if (warp == 1 && lane == 0) {
         // ---- producer: one 32 KB bulk copy for the A stage, one for the B stage ----
         const __half* atile = g.Ap + (((int64_t)blockIdx.x * g.nkb_total + kb0) << 14);
-        const __half* btile = g.Bp + (int64_t)kb0 * (b_bytes / 2);
+        const int64_t slot = b_slot_halves(g.Np);
+        const __half* btile = g.Bp + ((int64_t)pt * g.nkb_total + kb0) * slot;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&bar_free[s], (uint32_t)(((kb / STAGES) - 1) & 1));   // its MMAs have drained
             const uint32_t sa = sbase + (uint32_t)s * stage_bytes;
-            mbar_expect_tx(&bar_full[s], stage_bytes);
+            mbar_expect_tx(&bar_full[s], a_bytes + b_bytes);
             bulk_g2s(sa, atile + ((int64_t)kb << 14), a_bytes, &bar_full[s]);
-            bulk_g2s(sa + a_bytes, btile + (int64_t)kb * (b_bytes / 2), b_bytes, &bar_full[s]);
+            bulk_g2s(sa + a_bytes, btile + (int64_t)kb * slot, b_bytes, &bar_full[s]);
         }
     } else if (warp == 0) {
         // ---- MMA issuer ----
         const uint32_t leader = elect_one();
-        const uint32_t idesc = make_idesc_f16(128, (int)g.Np, /*b_mn_major=*/true);
+        const uint32_t idesc = make_idesc_f16(128, (int)w, /*b_mn_major=*/true);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&bar_full[s], (uint32_t)((kb / STAGES) & 1));
@@ -213,10 +222,11 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
     // epilogue: TMEM lane = output row; each thread writes its row's N partial sums
     {
         const int64_t m = m0 + 32 * warp + lane;
-        float* dst = g.partial + ((int64_t)z * g.M + (m < g.M ? m : 0)) * g.N;
+        float* dst = g.partial + ((int64_t)z * g.M + (m < g.M ? m : 0)) * g.N + (int64_t)pt * TG_BN;
+        const int ncols = (int)(g.N - (int64_t)pt * TG_BN);          // logical columns left from this tile's first one
         const uint32_t lane_addr = tbase + ((uint32_t)(32 * warp) << 16);
         const bool vec = (g.N % 4 == 0);
-        for (int c0 = 0; c0 < (int)g.Np; c0 += 16) {
+        for (int c0 = 0; c0 < (int)w; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(lane_addr + (uint32_t)c0, v);
             tmem_wait_ld();
@@ -224,13 +234,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_splitk_kernel(GemmArgs 
                 if (vec) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
-                        if (c0 + j < g.N)
+                        if (c0 + j < ncols)
                             *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < g.N) dst[c0 + j] = __uint_as_float(v[j]);
+                        if (c0 + j < ncols) dst[c0 + j] = __uint_as_float(v[j]);
                 }
             }
         }
@@ -284,7 +294,8 @@ __device__ __forceinline__ float4 reduce4(const float* __restrict__ partial, int
     return make_float4(s[0], s[1], s[2], s[3]);
 }
 // patches 4*n4 .. 4*n4+3 of row `row` -> 8 bytes of each piece
-__device__ __forceinline__ void store_pieces4(__half* __restrict__ Bp, int64_t row, int64_t n4, int64_t Np, const float (&v)[4]) {
+__device__ __forceinline__ void store_pieces4(__half* __restrict__ Bp, int64_t row, int64_t n4, int64_t Np, int64_t nkb,
+                                              const float (&v)[4]) {
     uint32_t w1[2], w2[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
@@ -294,17 +305,18 @@ __device__ __forceinline__ void store_pieces4(__half* __restrict__ Bp, int64_t r
         w1[j] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
         w2[j] = (uint32_t)__half_as_ushort(a2) | ((uint32_t)__half_as_ushort(b2) << 16);
     }
-    // k block, patch group of 8, k within the block, half of the 16-byte chunk
-    __half* t = Bp + (row >> 6) * (2 * Np * 64) + (n4 >> 1) * 512 + (row & 63) * 8 + (n4 & 1) * 4;
+    // patch tile, k block, patch group of 8 within the tile, k within the block, half of the 16-byte chunk
+    const int64_t p0 = 4 * n4, pt = p0 / TG_BN, pl = p0 - pt * TG_BN;
+    __half* t = Bp + (pt * nkb + (row >> 6)) * b_slot_halves(Np) + (pl >> 3) * 512 + (row & 63) * 8 + ((pl >> 2) & 1) * 4;
     *reinterpret_cast<uint2*>(t) = make_uint2(w1[0], w1[1]);
-    *reinterpret_cast<uint2*>(t + Np * 64) = make_uint2(w2[0], w2[1]);
+    *reinterpret_cast<uint2*>(t + ptile_width(Np, pt) * 64) = make_uint2(w2[0], w2[1]);
 }
 
 // r = m .* (y - D alpha)  -> r pieces (the division by the step constant happens after D^T r, in f2)
 __global__ void reduce_residual_kernel(const float* __restrict__ partial, int splits, int64_t n, int64_t P, int64_t Np,
                                        const float* __restrict__ Y, const float* __restrict__ BC,
                                        const float* __restrict__ f1, const float* __restrict__ sR,
-                                       __half* __restrict__ B2p) {
+                                       __half* __restrict__ B2p, int64_t nkb) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -317,7 +329,7 @@ __global__ void reduce_residual_kernel(const float* __restrict__ partial, int sp
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         v[j] = (j < cnt && BC[e0 + j] != 0.0f) ? (Y[e0 + j] - s[j] * f1[p0 + j]) * sR[p0 + j] : 0.0f;
-    store_pieces4(B2p, i, n4, Np, v);
+    store_pieces4(B2p, i, n4, Np, nkb, v);
 }
 
 // g = alpha + D^T r / a ;  GRAD_SOFT: alpha <- soft(g, T) (ista.m:21-23) ; GRAD_IDENTITY: alpha <- g ; both emit the
@@ -326,7 +338,8 @@ enum { GRAD_SOFT = 0, GRAD_IDENTITY = 1, GRAD_PLAIN = 2 };
 template <int MODE>
 __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int splits, int64_t K, int64_t P, int64_t Np,
                                        float* __restrict__ A, const float* __restrict__ T, const float* __restrict__ f2,
-                                       const float* __restrict__ sA, __half* __restrict__ B1p, float* __restrict__ G) {
+                                       const float* __restrict__ sA, __half* __restrict__ B1p, float* __restrict__ G,
+                                       int64_t nkb) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     pdl_launch_dependents();
     pdl_wait();
@@ -350,19 +363,19 @@ __global__ void reduce_gradient_kernel(const float* __restrict__ partial, int sp
             }
         }
     }
-    if (MODE != GRAD_PLAIN) store_pieces4(B1p, k, n4, Np, v);
+    if (MODE != GRAD_PLAIN) store_pieces4(B1p, k, n4, Np, nkb, v);
 }
 
 // pieces of a coefficient matrix that another kernel produced (the NLM denoiser)
 __global__ void alpha_pieces_kernel(const float* __restrict__ A, int64_t K, int64_t P, int64_t Np, const float* __restrict__ sA,
-                                    __half* __restrict__ B1p) {
+                                    __half* __restrict__ B1p, int64_t nkb) {
     const int64_t nb4 = Np / 4, t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= K * nb4) return;
     const int64_t k = t / nb4, n4 = t - k * nb4, p0 = 4 * n4, e0 = k * P + p0;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = p0 + j < P ? A[e0 + j] * sA[p0 + j] : 0.f;
-    store_pieces4(B1p, k, n4, Np, v);
+    store_pieces4(B1p, k, n4, Np, nkb, v);
 }
 
 // Phi_z = D alpha (full dictionary, main_LRS_PnP.py:294)
@@ -377,15 +390,17 @@ __global__ void reduce_store_kernel(const float* __restrict__ partial, int split
 
 struct Plan {
     int64_t Mp1, Kp1, Mp2, Kp2, Np;
+    int ntiles;             // patch tiles of TG_BN columns
     int S1, kb1, S2, kb2;   // splits and k blocks per split of both products
     size_t off_A, off_vec, off_dmax, off_A1, off_A2, off_B1, off_B2, off_part, off_G, total;
 };
 
 size_t al256(size_t b) { return (b + 255) / 256 * 256; }
 
-void choose_splits(int64_t Mp, int64_t Kp, int sms, int& S, int& kb_per) {
-    const int mt = (int)(Mp / TG_BM), nkb = (int)(Kp / TG_BK);
-    int s = sms / mt;
+void choose_splits(int64_t Mp, int64_t Kp, int ntiles, int sms, int& S, int& kb_per) {
+    const int64_t mt = Mp / TG_BM * ntiles;   // output tiles; split k only as far as one wave of CTAs allows
+    const int nkb = (int)(Kp / TG_BK);
+    int s = (int)(sms / mt);
     if (s < 1) s = 1;
     if (s > nkb) s = nkb;
     kb_per = (nkb + s - 1) / s;
@@ -399,8 +414,9 @@ Plan make_plan(int n, int K, int64_t P, int sms) {
     pl.Mp2 = round_up(K, TG_BM);
     pl.Kp2 = round_up(n, TG_BK);
     pl.Np = round_up(P, 16);
-    choose_splits(pl.Mp1, pl.Kp1, sms, pl.S1, pl.kb1);
-    choose_splits(pl.Mp2, pl.Kp2, sms, pl.S2, pl.kb2);
+    pl.ntiles = (int)((pl.Np + TG_BN - 1) / TG_BN);
+    choose_splits(pl.Mp1, pl.Kp1, pl.ntiles, sms, pl.S1, pl.kb1);
+    choose_splits(pl.Mp2, pl.Kp2, pl.ntiles, sms, pl.S2, pl.kb2);
     size_t o = 0;
     pl.off_A = o;
     o += al256((size_t)K * P * 4);
@@ -413,9 +429,9 @@ Plan make_plan(int n, int K, int64_t P, int sms) {
     pl.off_A2 = o;
     o += al256((size_t)2 * pl.Mp2 * pl.Kp2 * 2);
     pl.off_B1 = o;
-    o += al256((size_t)2 * pl.Kp1 * pl.Np * 2);
+    o += al256((size_t)pl.ntiles * (pl.Kp1 / TG_BK) * b_slot_halves(pl.Np) * 2);
     pl.off_B2 = o;
-    o += al256((size_t)2 * pl.Kp2 * pl.Np * 2);
+    o += al256((size_t)pl.ntiles * (pl.Kp2 / TG_BK) * b_slot_halves(pl.Np) * 2);
     pl.off_part = o;
     const size_t p1 = (size_t)pl.S1 * n * P * 4, p2 = (size_t)pl.S2 * K * P * 4;
     o += al256(p1 > p2 ? p1 : p2);
@@ -430,7 +446,7 @@ constexpr int PLAN_SMS = 148;   // the workspace size must not depend on the dev
 }  // namespace
 
 // Shapes the engine takes: a patch count that fits one MMA (N <= 256) and operands big enough to be worth the pieces.
-bool ista_tc_shape_ok(int n, int K, int64_t P) { return P >= 8 && P <= 256 && n >= 128 && K >= 128; }
+bool ista_tc_shape_ok(int n, int K, int64_t P) { return P >= 8 && P <= (int64_t)65535 * TG_BN && n >= 128 && K >= 128; }
 
 size_t ista_tc_workspace_bytes(int n, int K, int64_t P) { return ista_tc_shape_ok(n, K, P) ? make_plan(n, K, P, PLAN_SMS).total : 0; }
 
@@ -462,17 +478,17 @@ static cudaError_t launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block,
 
 template <int STAGES>
 static int launch_tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
-    const size_t smem = (size_t)STAGES * (2 * A_PIECE + 2 * (size_t)g.Np * 128);
+    const size_t smem = (size_t)STAGES * (2 * A_PIECE + (size_t)b_slot_halves(g.Np) * 2);
     int rc = check_cuda(fn, cudaFuncSetAttribute(tc_gemm_splitk_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
-    dim3 grid((unsigned)(g.Mp / TG_BM), (unsigned)splits);
+    dim3 grid((unsigned)(g.Mp / TG_BM), (unsigned)splits, (unsigned)((g.Np + TG_BN - 1) / TG_BN));
     rc = check_cuda(fn, launch_chained(tc_gemm_splitk_kernel<STAGES>, grid, dim3(TG_THREADS), smem, st, g));
     note_launch();
     return rc;
 }
 
 static int tc_gemm(const char* fn, const GemmArgs& g, int splits, cudaStream_t st) {
-    const size_t stage = 2 * A_PIECE + 2 * (size_t)g.Np * 128;
+    const size_t stage = 2 * A_PIECE + (size_t)b_slot_halves(g.Np) * 2;
     return 3 * stage <= 220 * 1024 ? launch_tc_gemm<3>(fn, g, splits, st) : launch_tc_gemm<2>(fn, g, splits, st);
 }
 
@@ -517,29 +533,29 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
     for (int it = 0; it < Nit; ++it) {
         if ((rc = tc_gemm(fn, g1, pl.S1, st)) != LRS_OK) return rc;
         rc = check_cuda(fn, launch_chained(reduce_residual_kernel, dim3(eb1), dim3(64), 0, st, (const float*)part, pl.S1, (int64_t)n, P,
-                                           pl.Np, blocks, blocks_copy, (const float*)f1, (const float*)sR, B2));
+                                           pl.Np, blocks, blocks_copy, (const float*)f1, (const float*)sR, B2, pl.Kp2 / TG_BK));
         note_launch();
         if (rc != LRS_OK) return rc;
         if ((rc = tc_gemm(fn, g2, pl.S2, st)) != LRS_OK) return rc;
         if (denoiser == LRS_DENOISE_SOFT) {
             rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_SOFT>, dim3(eb2), dim3(64), 0, st, (const float*)part, pl.S2,
                                                (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1,
-                                               (float*)nullptr));
+                                               (float*)nullptr, pl.Kp1 / TG_BK));
             note_launch();
             if (rc != LRS_OK) return rc;
         } else if (denoiser == LRS_DENOISE_IDENTITY) {
             rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_IDENTITY>, dim3(eb2), dim3(64), 0, st, (const float*)part,
                                                pl.S2, (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1,
-                                               (float*)nullptr));
+                                               (float*)nullptr, pl.Kp1 / TG_BK));
             note_launch();
             if (rc != LRS_OK) return rc;
         } else {
             rc = check_cuda(fn, launch_chained(reduce_gradient_kernel<GRAD_PLAIN>, dim3(eb2), dim3(64), 0, st, (const float*)part, pl.S2,
-                                               (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1, Gd));
+                                               (int64_t)K, P, pl.Np, A, (const float*)T, (const float*)f2, (const float*)sA, B1, Gd, pl.Kp1 / TG_BK));
             note_launch();
             if (rc != LRS_OK) return rc;
             if ((rc = nlm_columns(fn, Gd, T, h_scale, K, P, A, st)) != LRS_OK) return rc;
-            alpha_pieces_kernel<<<eb2, 64, 0, st>>>(A, K, P, pl.Np, sA, B1);
+            alpha_pieces_kernel<<<eb2, 64, 0, st>>>(A, K, P, pl.Np, sA, B1, pl.Kp1 / TG_BK);
             LRS_CHECK_LAUNCH(fn);
         }
     }
