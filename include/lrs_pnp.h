@@ -111,7 +111,7 @@ int lrs_spectral_table_f32(const float* D_dev, int K, int bb, int step, float* t
  * then phi_z[:,p] = D alpha (full dictionary, :294/:302).  Patches with a_p <= 0 give alpha = 0.
  * Replaces the jj loop main_LRS_PnP.py:270-303 + ista :131-149 / ista.m:13-24.
  * coefs_dev [K,P] and phi_z_dev [n,P] may each be NULL.  Any n, K, P.
- * Engines (chosen per call, same results to <= 2e-5 relative, all denoisers): for 8 <= P <= 256 and n, K >= 128 (the 36x36-patch
+ * Engines (chosen per call, same results to <= 2e-5 relative, all denoisers): for P >= 8 and n, K >= 128 (the 36x36-patch
  * configurations) the two products of an iteration run as split-K tcgen05 GEMMs with a 3-pass fp16 operand split
  * (ista_tc.cu); every other shape, and the environment override LRS_ISTA_ENGINE=simt, uses the fp32 FFMA kernels.
  * lrs_ista_workspace_bytes covers whichever engine the shape may take. */
