@@ -1,10 +1,12 @@
-// Tensor-core engine of the explicit ISTA path (lrs_ista_pnp_f32 with the soft denoiser) for the LARGE-PATCH regime of
-// the bundled configurations: n = bb^2 = 1296 pixels, K ~ 2592 atoms, P = 144 patches (main_LRS_PnP.py:131-149,
-// 270-303; ista.m:13-24).  There the dictionary (13 MB) does not fit on chip and the two products of an iteration,
+// Tensor-core engine of the explicit ISTA path (lrs_ista_pnp_f32: soft, NLM or identity update) for the LARGE-PATCH
+// regime of the bundled configurations: n = bb^2 = 1296 pixels, K ~ 2592 atoms, P = 144 patches (main_LRS_PnP.py:131-149,
+// 270-303; ista.m:13-24; 2304 patches for the 144 x 144 crop of main_LRS_PnP.m).  There the dictionary (13 MB) does not
+// fit on chip and the two products of an iteration,
 //     D alpha  [n x P] = D [n x K]  alpha [K x P]          and          D^T r  [K x P] = D^T [K x n]  r [n x P],
-// are tall-skinny GEMMs against a 144-column operand.  Each runs as ONE split-K launch of tcgen05 MMAs (M = 128 rows
-// per CTA, N = P <= 256, fp32 accumulators in TMEM) followed by a small reduce kernel that adds the split-K slices in a
-// fixed order and applies the fused epilogue (mask + residual, or gradient step + soft threshold).
+// are tall-skinny GEMMs against a few-hundred-column operand.  Each runs as ONE split-K launch of tcgen05 MMAs (M = 128
+// rows per CTA, N = up to 256 patches per CTA, fp32 accumulators in TMEM) followed by a small reduce kernel that adds the
+// split-K slices in a fixed order and applies the fused epilogue (mask + residual, or gradient step + soft threshold).
+// The launches of a call are chained with programmatic dependent launch.
 //
 // fp32 accuracy comes from the same 3-pass fp16 operand split as the fused engine (sparse_fused_tc.cu):
 //   x = x1 + x2, x1 = fp16(x), x2 = fp16(x - x1);   a b ~ a1 b1 + a2 b1 + a1 b2   (fp32 accumulate).
