@@ -93,3 +93,19 @@ def test_stripe_partition():
             # local stride-1 geometry has exactly the owned patch row-starts
             assert st.rows_local - bb + 1 == st.b - st.a
         assert owned == R
+
+
+def test_ista_workspace_covers_both_engines():
+    """lrs_ista_workspace_bytes is pure host arithmetic (no GPU): it must cover the FFMA engine everywhere and the fp16
+    operand pieces of the tensor-core engine on the shapes that engine takes (n, K >= 128, P >= 8)."""
+    from lrs_pnp_dip_b200 import _lib
+
+    L = _lib.lib()
+    al = lambda b: (b + 255) // 256 * 256
+    for n, K, P in ((64, 256, 5000), (1296, 2592, 144), (1296, 2592, 2304), (36, 80, 33), (128, 128, 8)):
+        need = L.lrs_ista_workspace_bytes(n, K, P)
+        assert need >= 2 * al(K * P * 4) + al(n * P * 4) + 2 * al(P * 4)
+        if n >= 128 and K >= 128 and P >= 8:
+            pieces = 2 * 2 * n * K * 2                                         # hi/lo pieces of D and of its transpose
+            assert need >= pieces + 2 * (K + n) * P * 2                        # + hi/lo pieces of alpha and r
+    assert L.lrs_ista_workspace_bytes(0, 5, 5) == 0 and L.lrs_ista_workspace_bytes(5, 5, -1) == 0
