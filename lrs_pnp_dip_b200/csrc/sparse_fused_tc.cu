@@ -49,6 +49,14 @@ constexpr int NPX = 16 / NCG;                  // pixels of every 16-pixel GEMM-
 static_assert(NPX == 8, "the residual epilogue moves its pixels with 8-column TMEM loads and 16-byte stores");
 constexpr int FIRST_EPI = (NEPI == 8) ? 4 : 2; // first epilogue warp (keeps warp % 4 == TMEM lane quarter)
 constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
+#ifndef LRS_WG0_REGS
+#define LRS_WG0_REGS 88
+#define LRS_EPI_REGS 208
+#endif
+#define LRS_STR2(x) #x
+#define LRS_STR(x) LRS_STR2(x)
+static_assert(128 * LRS_WG0_REGS + 256 * LRS_EPI_REGS <= 384 * 168, "register budget of one CTA per SM");
+static_assert(FIRST_EPI == 4 && NEPI == 8, "setmaxnreg works on warpgroups: warps 0-3 give registers to warps 4-11");
 constexpr int MAXCHUNK = 4;                    // soft-threshold / GEMM-A pipeline: K/64 chunks of 64 atoms, K <= 256
 constexpr uint32_t COL_ALPHA = 0;    // [0,256)   fp32 state / GEMM-B accumulator
 constexpr uint32_t COL_ACC = 256;    // [256,320) a1 D1 + a2 D1 ; [320,384) a1 D2
@@ -316,6 +324,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = sh.tmem_base;
+    // warp-specialised register budget: the MMA / gather warpgroup (warps 0-3) gives registers to the two epilogue
+    // warpgroups (168 each at launch: 128*88 + 256*208 = 384*168; 56/224 .. 104/200 measure the same within noise)
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 " LRS_STR(LRS_WG0_REGS) ";");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 " LRS_STR(LRS_EPI_REGS) ";");
 
     if (warp == 0) {
         // ================================ MMA issuer ================================
@@ -476,8 +488,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 for (int ks = 0; ks < 4; ++ks) {             // pixel quarter = GEMM-B k-step; my NPX pixels of it
                     uint32_t p1[NPX / 2], p2[NPX / 2];
                     if (it > 0) {
-                        // (prefetching the next quarter's accumulators here was measured: 664 ms vs 654 ms — the extra
-                        //  registers spill inside the iteration loop)
                         uint32_t b0[NPX], b1[NPX];
                         tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
                         tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
