@@ -1,14 +1,15 @@
-// Fused sparse-coding step on the implicit patch set — tcgen05 / TMEM engine (bb = 8, n = 64, K = 256).
+// Fused sparse-coding step on the implicit patch set — tcgen05 / TMEM engine (bb = 8, n = 64, K in {64,128,192,256}).
 //
 // Same contract as the FFMA engine (sparse_fused_simt.cu): for every selected 8x8 window of the unfolded
 // matrix run Nit soft-ISTA iterations against D and write Phi_z = D alpha (main_LRS_PnP.py:259-303,
 // ista.m:13-24).  Here the two contractions of every iteration run on the 5th-generation tensor cores:
 //
-//   tile        128 consecutive patches (reference order) = the 128 TMEM lanes = MMA M
-//   GEMM-B      G[128 x 256]  = alpha + r D        accumulated IN PLACE onto the fp32 state in TMEM
-//   epilogue    alpha = soft(G, T)                 tcgen05.ld -> registers -> tcgen05.st
+//   tile        128 consecutive row starts of one column start = the 128 TMEM lanes = MMA M
+//   GEMM-B      G[128 x K]    = alpha + r D        A operand = residual pieces in shared memory (SS form), two atom
+//                                                  halves, accumulated IN PLACE onto the fp32 state in TMEM
+//   epilogue    alpha = soft(G, T)                 tcgen05.ld -> registers -> tcgen05.st, 64-atom chunks
 //   GEMM-A      Da[128 x 64]  = alpha D^T          A operand = alpha pieces staged in TMEM (TS form)
-//   epilogue    r = m .* (y - Da) / a              written back to TMEM as the next A operand
+//   epilogue    r = m .* (y - Da / a)              fp16 pieces to shared memory, one 16-pixel k-step at a time
 //
 // so alpha (128 KB per tile) never leaves TMEM during the Nit iterations; HBM sees 3 gathers and one
 // Phi_z store per patch.
@@ -25,11 +26,12 @@
 // Each patch is normalised by an exact power of two (max |y| -> [0.5, 1)) so the fp16 pieces never leave
 // their range whatever the scale of the data; the result is scaled back exactly.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles; DESIGN.md 4.3-4.4 has the schedule and its history):
 //   warp 0      MMA issuer (whole warp runs the loop, one elected lane issues)
-//   warp 1      TMEM allocator
-//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and column group (w-4)/4 of every 64-column chunk
-//               (= 32 pixels of its patch).  NEPI = 16 (16 columns per thread) is supported but measured slower.
+//   warps 1-3   gather the NEXT tile's patch values into shared memory (warp 1 also owns the TMEM allocation)
+//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4).. and column group (w-4)/4 of every 64-column chunk and
+//               8 pixels of every 16-pixel GEMM-B k-step of its patch.  16 epilogue warps were measured slower.
+//   setmaxnreg moves registers from warps 0-3 (88 per thread) to warps 4-11 (208 per thread).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
