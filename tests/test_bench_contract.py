@@ -23,6 +23,14 @@ def test_reference_arm_json_line():
     assert "workload" in line["config"]
 
 
+def test_reference_arm_other_ranks_exit_silently():
+    """Under torchrun (N > 1) rank 0 alone runs the CPU reference arm; the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "mini",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_gpu_arm_fails_loudly_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "mini", "--steps", "1", "--warmup", "0"],
