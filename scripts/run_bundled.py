@@ -2,7 +2,7 @@
 dictionary (trained_dictionary.mat is not in the reference checkout): ms per outer iteration, ISTA
 patch-iterations/s of the sparse step, and the reference-formula MPSNR (main_LRS_PnP.py:379-384).
     python scripts/run_bundled.py [K]"""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import lrs_pnp_dip_b200 as lrs
