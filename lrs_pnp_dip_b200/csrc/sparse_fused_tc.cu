@@ -201,19 +201,30 @@ struct TilePlan {
     int cchunks, cpc;      // chunks per row block, column starts per chunk
 };
 
+// The walker also compiles for the host (lrs_debug_tile_walk below replays a launch's tile order on the CPU, so the
+// no-GPU test suite covers this integer logic); on the device the CTA index and the grid size stay special registers.
 struct TileWalk {
     int64_t item;
     int rb = 0, ci = 0, c_hi = 0;
+    int64_t stride_ = 0;                     // host replay only (never read on the device: optimised away)
     __device__ TileWalk() : item((int64_t)blockIdx.x - (int64_t)gridDim.x) {}
+    __host__ TileWalk(int64_t cta, int64_t grid) : item(cta - grid), stride_(grid) {}
+    __host__ __device__ __forceinline__ int64_t stride() const {
+#ifdef __CUDA_ARCH__
+        return gridDim.x;
+#else
+        return stride_;
+#endif
+    }
     // advance to this CTA's next tile holding at least one patch of [p_begin, p_end); pl and prm are the kernel
     // parameters (constant bank), so the walker itself only keeps four values live across the iteration loop
-    __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm) {
+    __host__ __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm) {
         const int64_t nR = prm.g.row.n;
         for (;;) {
             if (ci + 1 < c_hi) {
                 ++ci;
             } else {
-                item += gridDim.x;
+                item += stride();
                 if (item >= pl.items) return false;
                 rb = (int)(item / pl.cchunks);
                 ci = (int)(pl.ci0 + (item - (int64_t)rb * pl.cchunks) * pl.cpc);
@@ -235,7 +246,7 @@ struct PatchRef {
     int64_t p, pi, rs, cs;
     bool valid;
 };
-__device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, const TileWalk& tw, int m) {
+__host__ __device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, const TileWalk& tw, int m) {
     const int64_t nR = prm.g.row.n;
     int64_t ci = tw.ci, ri = (int64_t)tw.rb * TILE + m;
     int64_t p = ci * nR + ri;
@@ -667,18 +678,9 @@ bool sparse_fused_tc_supported(const FusedParams& prm, int K) {
     return major == 10;
 }
 
-template <int K>
-static int launch_tc(const FusedParams& prm, cudaStream_t st) {
-    const char* fn = "lrs_sparse_step_fused_f32";
-    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
-    static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
-    auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
-    int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (rc != LRS_OK) return rc;
-    int sms = device_sm_count();
-    if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
-    // work items: every row block of TILE row starts, cut into enough column-start chunks that the persistent grid
-    // stays balanced (>= ~100 items per SM when the problem has them) while a chunk still reuses its window.
+// work items: every row block of TILE row starts, cut into enough column-start chunks that the persistent grid stays
+// balanced (>= ~100 items per SM when the problem has them) while a chunk still reuses its window.
+static TilePlan make_tile_plan(const FusedParams& prm, int sms) {
     const int64_t nR = prm.g.row.n;
     TilePlan plan;
     plan.ci0 = prm.p_begin / nR;
@@ -689,6 +691,20 @@ static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     plan.cchunks = (int)cchunks;
     plan.cpc = (int)((ncols + cchunks - 1) / cchunks);
     plan.items = rblocks * cchunks;
+    return plan;
+}
+
+template <int K>
+static int launch_tc(const FusedParams& prm, cudaStream_t st) {
+    const char* fn = "lrs_sparse_step_fused_f32";
+    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
+    static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
+    auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
+    int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc != LRS_OK) return rc;
+    int sms = device_sm_count();
+    if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
+    const TilePlan plan = make_tile_plan(prm, sms);
     unsigned grid = (unsigned)(plan.items < sms ? plan.items : sms);
     kern<<<grid, NTHREADS, smem, st>>>(prm, plan);
     note_launch();
@@ -711,6 +727,34 @@ int tc_timing_read(unsigned long long* out32) {
 }
 
 }  // namespace lrs
+
+// Replays on the HOST the tile order a launch with `sms` SMs would use and counts how often every patch of
+// [p_begin, p_end) is owned by a valid lane (must be exactly once); idle lanes must point at a patch of the range.
+extern "C" int lrs_debug_tile_walk(int64_t R, int64_t C, int bb, int s, int64_t p_begin, int64_t p_end, int sms,
+                                   int* visits_host, int64_t* tiles_host) {
+    const char* fn = "lrs_debug_tile_walk";
+    lrs::FusedParams prm{};
+    if (bb != 8 || !lrs::make_geom(R, C, bb, s, prm.g)) return lrs::fail_arg(fn, "need bb = 8 and a valid geometry");
+    if (p_begin < 0 || p_end > prm.g.P || p_begin >= p_end || sms < 1 || !visits_host || !tiles_host)
+        return lrs::fail_arg(fn, "bad range, sms or null pointer");
+    prm.p_begin = p_begin;
+    prm.p_end = p_end;
+    const lrs::TilePlan plan = lrs::make_tile_plan(prm, sms);
+    const int64_t grid = plan.items < sms ? plan.items : sms;
+    int64_t tiles = 0;
+    for (int64_t cta = 0; cta < grid; ++cta) {
+        for (lrs::TileWalk tw(cta, grid); tw.next(plan, prm); ++tiles) {
+            for (int m = 0; m < lrs::TILE; ++m) {
+                const lrs::PatchRef pr = lrs::tile_patch(prm, tw, m);
+                if (pr.valid) ++visits_host[pr.pi];
+                if (pr.p < p_begin || pr.p >= p_end || pr.rs < 0 || pr.rs + bb > R || pr.cs < 0 || pr.cs + bb > C)
+                    return lrs::fail_arg(fn, "a lane points outside the patch range or the matrix");
+            }
+        }
+    }
+    *tiles_host = tiles;
+    return LRS_OK;
+}
 
 extern "C" int lrs_tc_timing_read(unsigned long long* out32_host) {
     if (!out32_host) return lrs::fail_arg("lrs_tc_timing_read", "null pointer");

@@ -109,3 +109,31 @@ def test_ista_workspace_covers_both_engines():
             pieces = 2 * 2 * n * K * 2                                         # hi/lo pieces of D and of its transpose
             assert need >= pieces + 2 * (K + n) * P * 2                        # + hi/lo pieces of alpha and r
     assert L.lrs_ista_workspace_bytes(0, 5, 5) == 0 and L.lrs_ista_workspace_bytes(5, 5, -1) == 0
+
+
+def test_fused_kernel_tile_walk_covers_every_patch_once():
+    """The persistent tcgen05 kernel walks (row block, column-start chunk) work items; lrs_debug_tile_walk replays that
+    integer logic on the host.  Every patch of the requested range must be owned by exactly one valid lane, for whole
+    ranges, sub-ranges cutting through columns and tiles, strides with appended starts and any SM count."""
+    from lrs_pnp_dip_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    cases = [(300, 20, 1, None, 148), (40, 23, 1, None, 148), (64, 41, 3, None, 148), (1500, 30, 1, None, 7),
+             (262144 // 64, 191, 1, None, 148), (9, 8, 5, None, 3), (8, 8, 1, None, 148), (50, 9, 20, None, 148)]
+    for _ in range(40):
+        R, Cc, s = int(rng.integers(8, 700)), int(rng.integers(8, 60)), int(rng.integers(1, 6))
+        cases.append((R, Cc, s, "random", int(rng.integers(1, 200))))
+    for R, Cc, s, mode, sms in cases:
+        P = lrs.ops.patch_count(R, Cc, 8, s)
+        ranges = [(0, P)]
+        if mode == "random" or P > 300:
+            a = int(rng.integers(0, P))
+            ranges += [(a, int(rng.integers(a + 1, P + 1))), (P - 1, P), (0, 1)]
+        for b, e in ranges:
+            visits = np.zeros(e - b, dtype=np.int32)
+            tiles = np.zeros(1, dtype=np.int64)
+            rc = L.lrs_debug_tile_walk(R, Cc, 8, s, b, e, sms, visits.ctypes.data, tiles.ctypes.data)
+            assert rc == 0, (L.lrs_last_error(), R, Cc, s, b, e, sms)
+            assert visits.min() == 1 and visits.max() == 1, (R, Cc, s, b, e, sms)
+            assert (e - b + 127) // 128 <= tiles[0] <= (e - b + 127) // 128 + 2 * (Cc - 7) + 2
