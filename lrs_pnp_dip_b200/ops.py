@@ -179,17 +179,17 @@ def row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
     n, K = D.shape
     assert n == bb * bb
     # The table depends on the dictionary only; the reference recomputes it per patch per outer iteration
-    # (main_LRS_PnP.py:134).  Cache per dictionary tensor (storage, version) so repeated calls reuse it.
-    Dd = D.double()
-    fingerprint = tuple(torch.stack([Dd.sum(), (Dd * Dd).sum(), Dd[0].sum(), Dd[:, 0].sum(), Dd[-1, -1]]).tolist())
-    key = (fingerprint, tuple(D.shape), str(D.device), bb, step)
+    # (main_LRS_PnP.py:134).  Cached per dictionary TENSOR: the key is (storage address, in-place version counter,
+    # shape, device) and the entry keeps a reference to the tensor, so the address cannot be recycled while the entry
+    # lives and any in-place write to D invalidates it.  No device synchronisation on a hit or a miss.
+    key = (D.data_ptr(), D._version, tuple(D.shape), tuple(D.stride()), str(D.device), bb, step)
     hit = _TABLE_CACHE.get(key)
     if hit is not None:
-        return hit
+        return hit[1]
     out = _row_pattern_table(D, bb, step)
     if len(_TABLE_CACHE) > 16:
         _TABLE_CACHE.clear()
-    _TABLE_CACHE[key] = out
+    _TABLE_CACHE[key] = (D, out)
     return out
 
 
@@ -255,7 +255,14 @@ def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "
 # ------------------------------------------------------------------ SVT
 def svt_weights(G: torch.Tensor, tau: float) -> torch.Tensor:
     """W = V diag(max(1 - tau/sigma, 0)) Vᵀ from the fp64 Gram matrix (σ² = eig)."""
-    evals, V = torch.linalg.eigh(G)
+    if not bool(torch.isfinite(G).all()):           # eigh synchronises anyway; this names the real cause
+        raise _lib.LrsError("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
+                            "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
+                            "with stride-1 overlap it grows geometrically and overflows fp32 after ~20 outer iterations)")
+    try:
+        evals, V = torch.linalg.eigh(G)
+    except RuntimeError as e:                       # torch.linalg.LinAlgError is a RuntimeError
+        raise _lib.LrsError(f"SVT: eigh of the {G.shape[0]}x{G.shape[0]} band Gram matrix failed: {e}") from e
     sigma = evals.clamp_min(0).sqrt()
     w = torch.where(sigma > tau, 1.0 - tau / sigma.clamp_min(1e-300), torch.zeros_like(sigma))
     return ((V * w[None, :]) @ V.T).to(torch.float32).contiguous()

@@ -95,6 +95,11 @@ class Stripe:
 
 def make_stripe(R: int, bb: int, rank: int, world: int) -> Stripe:
     bd = stripe_bounds(R, bb, world)
+    if world > 1 and int(np.diff(bd).min()) < bb - 1:
+        # halo_reduce / halo_refresh exchange the bb-1 halo rows with the IMMEDIATE neighbour only: a stripe that owns
+        # fewer rows than the halo would need a multi-hop exchange (contributions would be lost silently otherwise)
+        raise ValueError(f"row stripes of {int(np.diff(bd).min())} patch rows are narrower than the halo (bb-1 = {bb - 1}): "
+                         f"use at most {(R - bb + 1) // (bb - 1)} ranks for R = {R}")
     return Stripe(rank=rank, world=world, R_total=R, bb=bb, a=int(bd[rank]), b=int(bd[rank + 1]))
 
 
@@ -106,9 +111,14 @@ class SparseCoder:
     validity masks (``blocks_copy == 0``, main_LRS_PnP.py:244,276-280) and the ISTA step constants,
     which the reference recomputes for every patch in every outer iteration (:134)."""
 
-    def __init__(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str = "auto"):
+    def __init__(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str = "auto",
+                 defer_validation: bool = False):
+        """``defer_validation``: do not wait for the device-side input test (band-replicated masks for the
+        spectral table) at construction; its verdict is checked around the launches and by :meth:`validate`."""
         with _on(Y_observed):
             self._init(Y_observed, D, prm, engine)
+            if not defer_validation:
+                self.validate()
 
     def _init(self, Y_observed: torch.Tensor, D: torch.Tensor, prm: Params, engine: str):
         _lib.require_cuda()
@@ -125,12 +135,18 @@ class SparseCoder:
         self.engine = _lib.ENGINES[engine]
         self.fused = prm.bb == 8 and self.K in FUSED_K and prm.denoiser == "soft"
         self.a_patch = self.a_table = self.blocks_copy = None
+        self._bad_event = self._bad_host = None
         if self.fused:
             if prm.step == "spectral":
+                # The 256-entry table is indexed by the validity of the patch's 8 unfolded ROWS, which needs masks
+                # replicated over the bands (main_LRS_PnP.py:188-192).  The test runs on the device and its verdict
+                # travels to pinned host memory asynchronously: no host synchronisation here; the flag is looked at
+                # (without waiting) around every launch and (waiting) by validate().
                 obs = self.Y != 0
-                if not bool((obs == obs[:, :1]).all()):
-                    raise _lib.LrsError("spectral step constants on the fused path need band-replicated masks "
-                                        "(one validity flag per unfolded row); use step='frob4'")
+                self._bad_host = torch.empty((), dtype=torch.bool).pin_memory()
+                self._bad_host.copy_((obs != obs[:, :1]).any(), non_blocking=True)
+                self._bad_event = torch.cuda.Event()
+                self._bad_event.record()
                 self.a_table = ops.row_pattern_table(self.D, prm.bb, "spectral")
             elif prm.step != "frob4":
                 raise ValueError(prm.step)
@@ -138,10 +154,28 @@ class SparseCoder:
             self.blocks_copy = ops.im2col(self.Y, prm.bb, prm.slidingDis)
             self.a_patch = ops.step_constants(self.blocks_copy, self.D, prm.step)
 
+    def validate(self, wait: bool = True) -> None:
+        """Raise if the construction-time mask test failed.  ``wait=False`` only looks at a verdict that has
+        already arrived (no synchronisation)."""
+        ev = self._bad_event
+        if ev is None:
+            return
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._bad_event = None
+        if bool(self._bad_host):
+            raise _lib.LrsError("spectral step constants on the fused path need band-replicated masks "
+                                "(one validity flag per unfolded row); use step='frob4'")
+
     def phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         """Phi_z [n, P] of main_LRS_PnP.py:259-303 for V = X + lambda_1/mu_1."""
         with _on(X):
-            return self._phi_z(X, lambda_1)
+            self.validate(wait=False)
+            out = self._phi_z(X, lambda_1)
+            self.validate(wait=False)
+            return out
 
     def _phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         prm = self.prm
@@ -259,7 +293,7 @@ class CudaBackend:
     def __init__(self, Y_local: torch.Tensor, MtM_local: torch.Tensor, D: torch.Tensor, prm: Params, engine="auto"):
         self.prm = prm
         self.Y, self.MtM = Y_local, MtM_local
-        self.coder = SparseCoder(Y_local, D, prm, engine)
+        self.coder = SparseCoder(Y_local, D, prm, engine, defer_validation=True)
 
     def imout(self, X, lambda_1):
         return self.coder.imout(X, lambda_1)
@@ -320,6 +354,15 @@ class LRSPnP:
     def rows_owned(self) -> int:
         return self.stripe.rows_owned if self.stripe.world > 1 else self.Y.shape[0]
 
+    def reset(self) -> None:
+        """Back to the reference's initial state: X = Y_observed, λ1 = λ2 = 0 (main_LRS_PnP.py:219-220,229).
+        Three device copies/memsets on the current stream, no allocation."""
+        with _on(self.X):
+            self.X.copy_(self.Y)
+            self.lambda_1.zero_()
+            self.lambda_2.zero_()
+        self.iterations = 0
+
     def step(self) -> None:
         with _on(self.X):
             self._step()
@@ -344,7 +387,14 @@ class LRSPnP:
         self.comm.halo_refresh(self.X, self.lambda_1)
         self.iterations += 1
 
+    def validate(self) -> None:
+        """Wait for and check the deferred device-side input tests (see SparseCoder.validate)."""
+        coder = getattr(self.be, "coder", None)
+        if coder is not None:
+            coder.validate()
+
     def run(self, iteration_num: int) -> "LRSPnP":
         for _ in range(iteration_num):
             self.step()
+        self.validate()
         return self
