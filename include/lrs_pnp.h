@@ -80,6 +80,15 @@ int lrs_im2col_f32(const float* X_dev, const float* L_dev, float mu, int64_t R, 
  * sequential loop main_LRS_PnP.py:332-339).  Deterministic gather, no atomics. */
 int lrs_col2im_accum_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, int s, float* imout_dev,
                          lrs_stream_t stream);
+/* The same overlap sum fed one RANGE of column starts at a time (bb = 8, s = 1): blocks_dev holds only the patches
+ * p in [ci_begin*nR, ci_end*nR) (nR = R-bb+1 row starts; [n, (ci_end-ci_begin)*nR] row-major — what
+ * lrs_sparse_step_fused_f32 writes for that patch range) and imout_dev carries the running sum.  Patch order is
+ * column-start-outer (main_LRS_PnP.py:94-99), so calling with ascending, contiguous ranges that start at 0 continues
+ * every element's sequential fp32 sum exactly where the previous range left it: the result is bit-identical to
+ * lrs_col2im_accum_f32 on the whole Phi_z (main_LRS_PnP.py:332-339) without ever materialising it.  imout_dev needs no
+ * initialisation: an element's sum starts from 0 in the range that holds its first covering patch. */
+int lrs_col2im_accum_range_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, int s, int64_t ci_begin,
+                               int64_t ci_end, float* imout_dev, lrs_stream_t stream);
 /* Weight[R,C] of main_LRS_PnP.py:341 (analytic coverage count). */
 int lrs_coverage_weight_f32(int64_t R, int64_t C, int bb, int s, float* weight_dev, lrs_stream_t stream);
 

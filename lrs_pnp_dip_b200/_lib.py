@@ -34,6 +34,7 @@ SIGNATURES = {
     "lrs_patch_index_i64": (_int, [_i64, _i64, _int, _int, _p, _p, _p, _p]),
     "lrs_im2col_f32": (_int, [_p, _p, _f, _i64, _i64, _int, _int, _p, _p]),
     "lrs_col2im_accum_f32": (_int, [_p, _i64, _i64, _int, _int, _p, _p]),
+    "lrs_col2im_accum_range_f32": (_int, [_p, _i64, _i64, _int, _int, _i64, _i64, _p, _p]),
     "lrs_coverage_weight_f32": (_int, [_i64, _i64, _int, _int, _p, _p]),
     "lrs_soft_f32": (_int, [_p, _f, _p, _i64, _p]),
     "lrs_axpy_f32": (_int, [_p, _p, _f, _p, _i64, _p]),

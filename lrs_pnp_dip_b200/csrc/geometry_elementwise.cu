@@ -155,21 +155,31 @@ __device__ __forceinline__ float col2im_column(const Geom& g, const float* __res
 // Stride-1 specialisation (the dense-overlap geometry of cfg 4/5): no appended starts, no divisions, and for interior
 // rows the BB row starts of a column start are BB loads at compile-time multiples of one pointer step — about four
 // instructions per load instead of the generic path's 28 (ncu), which is what makes the kernel HBM-bound.
+//
+// Column-start RANGE mode: `blocks` holds only the patches of column starts [ci_begin, ci_end) (P = (ci_end - ci_begin) * nR
+// columns), and every output element covered by them CONTINUES its running fp32 sum from `out` — or starts it from 0 when
+// the range contains its first covering column start.  Patch order is column-start-outer, so feeding the ranges in
+// ascending order reproduces the association of the sequential loop (main_LRS_PnP.py:332-339) bit for bit while only one
+// range of Phi_z exists at a time.  Only output columns [ci_begin, ci_end + BB - 1) are touched.
 template <int BB, int JU, int MINB>
-__global__ void __launch_bounds__(256, MINB) col2im_s1_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out) {
+__global__ void __launch_bounds__(256, MINB) col2im_s1_kernel(Geom g, const float* __restrict__ blocks, float* __restrict__ out,
+                                                              int64_t ci_begin, int64_t ci_end) {
     __shared__ float tile[32][33];
-    const int64_t r0 = blockIdx.x * 32LL, c0 = blockIdx.y * 32LL;
+    const int64_t r0 = blockIdx.x * 32LL, c0 = ci_begin + blockIdx.y * 32LL;
     const int tx = threadIdx.x, ty = threadIdx.y;  // blockDim = (32, 8)
-    const int64_t nR = g.row.n, nC = g.col.n, P = g.P;
+    const int64_t nR = g.row.n, nC = g.col.n, P = (ci_end - ci_begin) * nR;
     const int64_t step = 1 - P, cstep = nR - (int64_t)BB * P;
+    const int64_t c_end = ci_end + BB - 1 < g.C ? ci_end + BB - 1 : g.C;   // one past the last output column touched
     for (int cc = ty; cc < 32; cc += 8) {
         const int64_t r = r0 + tx, c = c0 + cc;
         float sum = 0.0f;
-        if (r < g.R && c < g.C) {
+        if (r < g.R && c < c_end) {
             const int64_t rlo = r - (BB - 1) > 0 ? r - (BB - 1) : 0, rhi = r < nR - 1 ? r : nR - 1;
-            const int64_t clo = c - (BB - 1) > 0 ? c - (BB - 1) : 0, chi = c < nC - 1 ? c : nC - 1;
+            const int64_t clo_all = c - (BB - 1) > 0 ? c - (BB - 1) : 0, chi_all = c < nC - 1 ? c : nC - 1;
+            const int64_t clo = clo_all > ci_begin ? clo_all : ci_begin, chi = chi_all < ci_end - 1 ? chi_all : ci_end - 1;
             const int nreg = (int)(rhi - rlo + 1), ncol = (int)(chi - clo + 1);
-            const float* pc = blocks + ((r - rlo) + (int64_t)BB * (c - clo)) * P + clo * nR + rlo;
+            if (clo > clo_all) sum = out[r * g.C + c];        // earlier ranges already added this element's first patches
+            const float* pc = blocks + ((r - rlo) + (int64_t)BB * (c - clo)) * P + (clo - ci_begin) * nR + rlo;
             if (nreg == BB) {
                 int j = 0;
                 for (; j + JU <= ncol; j += JU) {   // JU column starts = JU*BB independent loads in flight
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(256, MINB) col2im_s1_kernel(Geom g, const floa
     __syncthreads();
     for (int rr = ty; rr < 32; rr += 8) {
         const int64_t r = r0 + rr, c = c0 + tx;
-        if (r < g.R && c < g.C) out[r * g.C + c] = tile[tx][rr];
+        if (r < g.R && c < c_end) out[r * g.C + c] = tile[tx][rr];
     }
 }
 
@@ -401,9 +411,26 @@ int lrs_col2im_accum_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, 
     if (grid.y > 65535) return fail_arg("lrs_col2im_accum_f32", "C too large");
     // measured at cfg 4 (B200): generic kernel 3.9 ms; stride-1 kernel 2.2-2.6 ms; two or four column starts in flight
     // per thread, 8 blocks/SM with 32 registers, or longer row tiles (128x8, 256x4) are all slower
-    if (s == 1 && bb == 8) col2im_s1_kernel<8, 1, 6><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
+    if (s == 1 && bb == 8)
+        col2im_s1_kernel<8, 1, 6><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev, 0, g.col.n);
     else col2im_kernel<32, 32, 8><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev);
     LRS_CHECK_LAUNCH("lrs_col2im_accum_f32");
+    return LRS_OK;
+}
+
+int lrs_col2im_accum_range_f32(const float* blocks_dev, int64_t R, int64_t C, int bb, int s, int64_t ci_begin, int64_t ci_end,
+                               float* imout_dev, lrs_stream_t stream) {
+    const char* fn = "lrs_col2im_accum_range_f32";
+    Geom g;
+    if (!make_geom(R, C, bb, s, g)) return fail_arg(fn, "need 0 < bb <= min(R,C) and s > 0");
+    if (s != 1 || bb != 8) return fail_arg(fn, "column-start ranges are implemented for bb = 8, stride 1 (the dense-overlap geometry)");
+    if (!blocks_dev || !imout_dev) return fail_arg(fn, "null pointer");
+    if (ci_begin < 0 || ci_end > g.col.n || ci_begin >= ci_end) return fail_arg(fn, "need 0 <= ci_begin < ci_end <= column starts");
+    const int64_t c_end = ci_end + bb - 1 < C ? ci_end + bb - 1 : C;
+    dim3 grid(blocks_for(R, 32), blocks_for(c_end - ci_begin, 32));
+    if (grid.y > 65535) return fail_arg(fn, "C too large");
+    col2im_s1_kernel<8, 1, 6><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(g, blocks_dev, imout_dev, ci_begin, ci_end);
+    LRS_CHECK_LAUNCH(fn);
     return LRS_OK;
 }
 

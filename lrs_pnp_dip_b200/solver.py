@@ -136,6 +136,7 @@ class SparseCoder:
         self.fused = prm.bb == 8 and self.K in FUSED_K and prm.denoiser == "soft"
         self.a_patch = self.a_table = self.blocks_copy = None
         self._bad_event = self._bad_host = None
+        self._bufs = self._streams = None
         if self.fused:
             if prm.step == "spectral":
                 # The 256-entry table is indexed by the validity of the patch's 8 unfolded ROWS, which needs masks
@@ -180,21 +181,78 @@ class SparseCoder:
     def _phi_z(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         prm = self.prm
         if self.fused:
-            phi = torch.empty((self.n, self.P), dtype=torch.float32, device=X.device)
-            check(lib().lrs_sparse_step_fused_f32(ptr(X), ptr(lambda_1), float(prm.mu_1), ptr(self.Y), ptr(self.D), self.K,
-                                                  ptr(self.a_patch), ptr(self.a_table), float(prm.lambda_ista), int(prm.Nit),
-                                                  self.R, self.C, prm.bb, prm.slidingDis, 0, self.P, ptr(phi),
-                                                  self.engine, stream_ptr()), "lrs_sparse_step_fused_f32")
-            return phi
+            return self._fused_range(X, lambda_1, 0, self.P)
         blocks = ops.im2col(X, prm.bb, prm.slidingDis, lambda_1, prm.mu_1)
         _, phi = ops.ista_batched(blocks, self.blocks_copy, self.D, self.a_patch, prm.lambda_ista, prm.Nit,
                                   denoiser=prm.denoiser, h_scale=prm.nlm_h_scale)
         return phi
 
+    def _fused_range(self, X, lambda_1, p_begin: int, p_end: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        prm = self.prm
+        if out is None:
+            out = torch.empty((self.n, p_end - p_begin), dtype=torch.float32, device=X.device)
+        check(lib().lrs_sparse_step_fused_f32(ptr(X), ptr(lambda_1), float(prm.mu_1), ptr(self.Y), ptr(self.D), self.K,
+                                              ptr(self.a_patch), ptr(self.a_table), float(prm.lambda_ista), int(prm.Nit),
+                                              self.R, self.C, prm.bb, prm.slidingDis, p_begin, p_end, ptr(out),
+                                              self.engine, stream_ptr()), "lrs_sparse_step_fused_f32")
+        return out
+
+    def phi_z_range(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor], p_begin: int, p_end: int) -> torch.Tensor:
+        """Phi_z columns [p_begin, p_end) only (patch numbering of main_LRS_PnP.py:94-99; fused engines)."""
+        if not self.fused:
+            raise _lib.LrsError("patch sub-ranges are served by the fused engines (bb = 8, K in 64/128/192/256, soft denoiser)")
+        if not 0 <= p_begin < p_end <= self.P:
+            raise ValueError(f"patch range [{p_begin}, {p_end}) outside [0, {self.P})")
+        with _on(X):
+            self.validate(wait=False)
+            return self._fused_range(X, lambda_1, int(p_begin), int(p_end))
+
+    # ---- overlap sum without materialising Phi_z ----
+    # Patch order is column-start-outer (main_LRS_PnP.py:94-99), so the sequential fp32 overlap sum (:332-339) can be
+    # continued range by range of column starts (lrs_col2im_accum_range_f32): only two ranges of Phi_z exist at a time.
+    # Two streams alternate: the fused kernel of range k+1 starts on the SMs range k frees while the overlap sum of
+    # range k runs; the sums themselves are chained by events because consecutive ranges share output columns.
+    CHUNK_BYTES = 768 << 20          # per Phi_z range buffer (two buffers): cfg 4 -> 12 column starts, cfg 5 -> 3
+
+    def _chunk_cols(self) -> int:
+        nR = self.R - self.prm.bb + 1
+        return max(1, int(self.CHUNK_BYTES // (nR * self.n * 4)))
+
     def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
         """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339)."""
+        prm = self.prm
         with _on(X):
-            return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, self.prm.bb, self.prm.slidingDis)
+            nC = self.C - prm.bb + 1
+            if not (self.fused and prm.slidingDis == 1) or self._chunk_cols() >= nC:
+                return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, prm.bb, prm.slidingDis)
+            self.validate(wait=False)
+            nR, cpc = self.R - prm.bb + 1, self._chunk_cols()
+            if self._bufs is None or self._bufs[0].device != X.device:
+                self._bufs = [torch.empty(self.n * cpc * nR, dtype=torch.float32, device=X.device) for _ in range(2)]
+                self._streams = [torch.cuda.Stream(device=X.device) for _ in range(2)]
+            out = torch.empty((self.R, self.C), dtype=torch.float32, device=X.device)
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            prev_sum = None
+            for k, c0 in enumerate(range(0, nC, cpc)):
+                c1 = min(nC, c0 + cpc)
+                st = self._streams[k & 1]
+                if k < 2:
+                    st.wait_event(ready)                      # inputs (and `out`) are ready on the caller's stream
+                with torch.cuda.stream(st):
+                    buf = self._bufs[k & 1][:self.n * (c1 - c0) * nR].view(self.n, (c1 - c0) * nR)
+                    self._fused_range(X, lambda_1, c0 * nR, c1 * nR, out=buf)   # buffer k&1 was released by sum k-2 (same stream)
+                    if prev_sum is not None:
+                        st.wait_event(prev_sum)               # running sum: range k continues where range k-1 stopped
+                    check(lib().lrs_col2im_accum_range_f32(ptr(buf), self.R, self.C, prm.bb, prm.slidingDis, c0, c1, ptr(out),
+                                                           stream_ptr()), "lrs_col2im_accum_range_f32")
+                    prev_sum = torch.cuda.Event()
+                    prev_sum.record(st)
+            for st in self._streams:
+                main.wait_stream(st)
+            self.validate(wait=False)
+            return out
 
 
 def sparse_step(X, lambda_1, mu_1, Y_observed, D, bb, slidingDis, lambda_ista, Nit, step="spectral", engine="auto",
