@@ -257,6 +257,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    if args.range_mb:
+        solver.SparseCoder.CHUNK_BYTES = args.range_mb << 20
     parity = sharded_parity(torch, dist, lrs, solver, rank, world, dev, args.engine) if world > 1 else None
 
     Y, pm, D = make_inputs(args.workload)
@@ -462,6 +464,8 @@ def main():
     ap.add_argument("--profile-range", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--range-mb", type=int, default=None,
+                    help="experiment: size (MiB) of each of the two Phi_z range buffers (default: SparseCoder.CHUNK_BYTES)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

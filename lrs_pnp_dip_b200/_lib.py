@@ -49,13 +49,19 @@ SIGNATURES = {
     "lrs_admm_update_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i64, _i64, _i64, _i64, _int, _int, _p]),
     "lrs_gram_f64": (_int, [_p, _p, _f, _i64, _i64, _p, _p]),
     "lrs_svt_apply_f32": (_int, [_p, _p, _f, _p, _i64, _i64, _p, _p]),
+}
+
+# diagnostics build only (include/lrs_pnp_diag.h, csrc/liblrs_pnp_diag.so): never loaded by the product path
+DIAG_SIGNATURES = {
     "lrs_tc_probe_f32": (_int, [_p, _p, _p, _int, _int, _int, _int, _int, _p]),
     "lrs_tc_timing_read": (_int, [C.POINTER(C.c_uint64)]),
     "lrs_debug_tile_walk": (_int, [_i64, _i64, _int, _int, _i64, _i64, _int, _p, _p]),
     "lrs_tc_microbench": (_int, [_int, _int, _int, _int, _int, _int, _int, _int, _int, _p, _p]),
 }
+DIAG_LIB_PATH = os.path.join(_HERE, "csrc", "liblrs_pnp_diag.so")
 
 _lib: Optional[C.CDLL] = None
+_diag: Optional[C.CDLL] = None
 
 
 class LrsError(RuntimeError):
@@ -65,6 +71,9 @@ class LrsError(RuntimeError):
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
+        if os.environ.get("LRS_PNP_DIAGNOSTICS") == "1":      # developer switch (scripts/tc_timing.py): instrumented build
+            _lib = diag_lib()
+            return _lib
         if not os.path.isfile(LIB_PATH):
             raise LrsError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -78,9 +87,25 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def check(rc: int, what: str = "") -> None:
+def diag_lib() -> C.CDLL:
+    """The diagnostics build (tests/ and scripts/ only): the product entry points compiled with -DLRS_DIAGNOSTICS plus
+    the tcgen05 probes, the host replay of the tile walk and the barrier-wait counters."""
+    global _diag
+    if _diag is None:
+        if not os.path.isfile(DIAG_LIB_PATH):
+            raise LrsError(f"{DIAG_LIB_PATH} not found: build it with `make -C lrs_pnp_dip_b200/csrc`")
+        L = C.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **DIAG_SIGNATURES}.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = L
+    return _diag
+
+
+def check(rc: int, what: str = "", L: Optional[C.CDLL] = None) -> None:
     if rc != 0:
-        msg = lib().lrs_last_error()
+        msg = (L or lib()).lrs_last_error()
         raise LrsError(f"{what or 'liblrs_pnp'} failed (code {rc}): {msg.decode() if msg else ''}")
 
 

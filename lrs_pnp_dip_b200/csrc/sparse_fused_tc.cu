@@ -688,9 +688,9 @@ static TilePlan make_tile_plan(const FusedParams& prm, int sms) {
     const int64_t ncols = plan.ci_end - plan.ci0, rblocks = (nR + TILE - 1) / TILE;
     int64_t cchunks = (100 * (int64_t)sms + rblocks - 1) / rblocks;
     cchunks = cchunks < 1 ? 1 : (cchunks > ncols ? ncols : cchunks);
-    plan.cchunks = (int)cchunks;
     plan.cpc = (int)((ncols + cchunks - 1) / cchunks);
-    plan.items = rblocks * cchunks;
+    plan.cchunks = (int)((ncols + plan.cpc - 1) / plan.cpc);   // no empty chunks: every work item holds tiles
+    plan.items = rblocks * plan.cchunks;
     return plan;
 }
 
@@ -698,8 +698,12 @@ template <int K>
 static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
+#ifdef LRS_DIAGNOSTICS   // liblrs_pnp_diag.so only: barrier-wait counters (include/lrs_pnp_diag.h)
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
     auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
+#else
+    auto kern = sparse_fused_tc_kernel<false, K>;
+#endif
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
     int sms = device_sm_count();
@@ -722,11 +726,16 @@ int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
     }
 }
 
+#ifdef LRS_DIAGNOSTICS
 int tc_timing_read(unsigned long long* out32) {
     return check_cuda("lrs_tc_timing_read", cudaMemcpyFromSymbol(out32, g_tc_timing, sizeof(unsigned long long) * 32));
 }
+#endif
 
 }  // namespace lrs
+
+#ifdef LRS_DIAGNOSTICS
+#include "../../include/lrs_pnp_diag.h"
 
 // Replays on the HOST the tile order a launch with `sms` SMs would use and counts how often every patch of
 // [p_begin, p_end) is owned by a valid lane (must be exactly once); idle lanes must point at a patch of the range.
@@ -760,3 +769,4 @@ extern "C" int lrs_tc_timing_read(unsigned long long* out32_host) {
     if (!out32_host) return lrs::fail_arg("lrs_tc_timing_read", "null pointer");
     return lrs::tc_timing_read(out32_host);
 }
+#endif  // LRS_DIAGNOSTICS

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "../../include/lrs_pnp_diag.h"
 
 namespace lrs {
 using namespace tc;

@@ -106,6 +106,35 @@ def make_stripe(R: int, bb: int, rank: int, world: int) -> Stripe:
 # --------------------------------------------------------------------------------------------------
 # sparse-coding step
 # --------------------------------------------------------------------------------------------------
+class _RangePipe:
+    """Per-device resources of the range-wise overlap sum (SparseCoder.imout): two side streams and two Phi_z range
+    buffers, shared by every SparseCoder on the device.  Buffer i is only ever touched on stream i, so stream order
+    alone serialises successive users; nothing is allocated or created per call."""
+
+    def __init__(self, device):
+        self.device = device
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+        self.bufs = None
+
+    def buffers(self, numel: int):
+        if self.bufs is None or self.bufs[0].numel() < numel:
+            for st in self.streams:              # growing (rare): pending work on the old buffers must finish first
+                st.synchronize()
+            self.bufs = None
+            self.bufs = [torch.empty(numel, dtype=torch.float32, device=self.device) for _ in range(2)]
+        return self.bufs
+
+
+_RANGE_PIPES: dict = {}
+
+
+def _range_pipe(device) -> _RangePipe:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _RANGE_PIPES:
+        _RANGE_PIPES[key] = _RangePipe(torch.device("cuda", key))
+    return _RANGE_PIPES[key]
+
+
 class SparseCoder:
     """Everything of the sparse step that depends only on (Y_observed, D, geometry): the per-patch
     validity masks (``blocks_copy == 0``, main_LRS_PnP.py:244,276-280) and the ISTA step constants,
@@ -136,7 +165,6 @@ class SparseCoder:
         self.fused = prm.bb == 8 and self.K in FUSED_K and prm.denoiser == "soft"
         self.a_patch = self.a_table = self.blocks_copy = None
         self._bad_event = self._bad_host = None
-        self._bufs = self._streams = None
         if self.fused:
             if prm.step == "spectral":
                 # The 256-entry table is indexed by the validity of the patch's 8 unfolded ROWS, which needs masks
@@ -227,9 +255,8 @@ class SparseCoder:
                 return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, prm.bb, prm.slidingDis)
             self.validate(wait=False)
             nR, cpc = self.R - prm.bb + 1, self._chunk_cols()
-            if self._bufs is None or self._bufs[0].device != X.device:
-                self._bufs = [torch.empty(self.n * cpc * nR, dtype=torch.float32, device=X.device) for _ in range(2)]
-                self._streams = [torch.cuda.Stream(device=X.device) for _ in range(2)]
+            pipe = _range_pipe(X.device)
+            bufs, streams = pipe.buffers(self.n * cpc * nR), pipe.streams
             out = torch.empty((self.R, self.C), dtype=torch.float32, device=X.device)
             main = torch.cuda.current_stream()
             ready = torch.cuda.Event()
@@ -237,11 +264,11 @@ class SparseCoder:
             prev_sum = None
             for k, c0 in enumerate(range(0, nC, cpc)):
                 c1 = min(nC, c0 + cpc)
-                st = self._streams[k & 1]
+                st = streams[k & 1]
                 if k < 2:
                     st.wait_event(ready)                      # inputs (and `out`) are ready on the caller's stream
                 with torch.cuda.stream(st):
-                    buf = self._bufs[k & 1][:self.n * (c1 - c0) * nR].view(self.n, (c1 - c0) * nR)
+                    buf = bufs[k & 1][:self.n * (c1 - c0) * nR].view(self.n, (c1 - c0) * nR)
                     self._fused_range(X, lambda_1, c0 * nR, c1 * nR, out=buf)   # buffer k&1 was released by sum k-2 (same stream)
                     if prev_sum is not None:
                         st.wait_event(prev_sum)               # running sum: range k continues where range k-1 stopped
@@ -249,7 +276,7 @@ class SparseCoder:
                                                            stream_ptr()), "lrs_col2im_accum_range_f32")
                     prev_sum = torch.cuda.Event()
                     prev_sum.record(st)
-            for st in self._streams:
+            for st in streams:
                 main.wait_stream(st)
             self.validate(wait=False)
             return out

@@ -4,11 +4,11 @@ hot path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 product package never does.
 
 Parity status: PINNED.  Every function below is checked in
-``tests/test_oracle_vs_reference.py`` against the reference's own functions
-executed literally (``oracle/ref_extract.py``) when ``/root/reference`` is
-present, and against the committed fixtures those functions produced
-(``tests/golden/*.npz``, generator ``tests/golden/make_golden.py``) everywhere
-else.  The one unpinned piece of the reference is the skimage NLM denoiser
+``tests/test_oracle.py`` and ``tests/test_configs_parity.py`` against the
+reference's own functions executed literally (``oracle/ref_extract.py``) when
+``/root/reference`` is present, and against the committed fixtures those
+functions produced (``tests/golden/*.npz``, generators
+``tests/golden/make_golden.py`` and ``make_golden_r2.py``) everywhere else.  The one unpinned piece of the reference is the skimage NLM denoiser
 (third-party, absent, version unpinned — SURVEY §8c); the denoiser restated
 here is the MATLAB twin's soft threshold (ista.m:23, soft.m:4), which is the
 update BASELINE.json's north_star names.

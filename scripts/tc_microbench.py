@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lrs_pnp_dip_b200 import _lib
 
-L = _lib.lib()
+L = _lib.diag_lib()
 reps, blocks = 2048, 148
 def run(do_mma, f16, ts, N, nacc, ldst, depth):
     out = torch.zeros(blocks * 16, dtype=torch.int64, device="cuda")

@@ -2,6 +2,7 @@
     LRS_TC_TIMING=1 python scripts/tc_timing.py [rows] [bands]"""
 import ctypes, os, sys
 os.environ["LRS_TC_TIMING"] = "1"
+os.environ["LRS_PNP_DIAGNOSTICS"] = "1"      # the barrier-wait counters exist in liblrs_pnp_diag.so only
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import lrs_pnp_dip_b200 as lrs
@@ -21,7 +22,7 @@ for _ in range(2):
     sc.phi_z(Xd, None)
 torch.cuda.synchronize()
 buf = (ctypes.c_uint64 * 32)()
-_lib.check(_lib.lib().lrs_tc_timing_read(buf))
+_lib.check(_lib.diag_lib().lrs_tc_timing_read(buf))
 t = np.array(buf[:], dtype=np.float64)
 its = t[10]
 print(f"iterations (block 0): {its:.0f}; MMA-warp cycles/iter {t[0]/its:.0f}")

@@ -15,12 +15,12 @@ def tf32_trunc(x):
 def probe(A, B, a_in_tmem, b_mn, f16):
     from lrs_pnp_dip_b200 import _lib
 
-    L = _lib.lib()
+    L = _lib.diag_lib()          # probes live in the diagnostics build (include/lrs_pnp_diag.h)
     N, Kd = B.shape
     Ad, Bd = torch.tensor(A).cuda(), torch.tensor(B).cuda()
     C = torch.zeros((128, N), dtype=torch.float32, device="cuda")
     _lib.check(L.lrs_tc_probe_f32(Ad.data_ptr(), Bd.data_ptr(), C.data_ptr(), N, Kd, a_in_tmem, b_mn, f16,
-                                  torch.cuda.current_stream().cuda_stream), "lrs_tc_probe_f32")
+                                  torch.cuda.current_stream().cuda_stream), "lrs_tc_probe_f32", L)
     torch.cuda.synchronize()
     return C.cpu().numpy()
 

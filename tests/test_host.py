@@ -35,6 +35,23 @@ def test_library_exports_every_declared_symbol():
     assert L.lrs_version() >= 100
 
 
+def test_diagnostics_live_in_their_own_header_and_library():
+    """Probes, the tile-walk replay and the timing counters are declared in include/lrs_pnp_diag.h and exported by
+    liblrs_pnp_diag.so only: the product header / library carry none of them."""
+    import ctypes
+
+    hdr = open(os.path.join(ROOT, "include", "lrs_pnp_diag.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lrs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.DIAG_SIGNATURES), declared ^ set(_lib.DIAG_SIGNATURES)
+    prod = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert not hasattr(prod, name), f"{name} leaked into the product library"
+    D = _lib.diag_lib()
+    for name in declared | set(_lib.SIGNATURES):
+        assert hasattr(D, name), name
+
+
 @pytest.mark.parametrize("geom", [(1296, 128, 36, 36), (64, 41, 8, 3), (64, 40, 8, 8), (50, 23, 8, 1), (37, 19, 4, 3),
                                   (262144, 191, 8, 1), (20, 20, 3, 7), (8, 8, 8, 1)])
 def test_host_geometry_matches_oracle(geom):
@@ -117,7 +134,7 @@ def test_fused_kernel_tile_walk_covers_every_patch_once():
     ranges, sub-ranges cutting through columns and tiles, strides with appended starts and any SM count."""
     from lrs_pnp_dip_b200 import _lib
 
-    L = _lib.lib()
+    L = _lib.diag_lib()
     rng = np.random.default_rng(0)
     cases = [(300, 20, 1, None, 148), (40, 23, 1, None, 148), (64, 41, 3, None, 148), (1500, 30, 1, None, 7),
              (262144 // 64, 191, 1, None, 148), (9, 8, 5, None, 3), (8, 8, 1, None, 148), (50, 9, 20, None, 148)]
