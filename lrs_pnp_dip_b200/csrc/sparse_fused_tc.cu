@@ -477,7 +477,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             const bool ok_a = a > 0.0f;
             const float inv_a = ok_a ? __fdiv_rn(1.0f, a) : 0.0f;
             int ex = 0;
-            if (amax > 0.0f) (void)frexpf(amax, &ex);          // amax = f * 2^ex, f in [0.5, 1)
+            // amax = f * 2^ex, f in [0.5, 1).  Subnormal maxima are treated as 0 (2^-ex would overflow; such a patch is
+            // below fp32's normal range anyway and reconstructs to 0), and ex is capped so that 2^ex stays finite.
+            if (amax >= 1.17549435e-38f && amax < INFINITY) (void)frexpf(amax, &ex);
+            ex = ex > 127 ? 127 : ex;
             const float dn = ldexpf(1.0f, -ex), up = ldexpf(1.0f, ex);
             const float Tn = ok_a ? 0.5f * prm.lambda * dn * sd : 0.0f;  // a_h * T_h = lambda' sd / 2 (ista.m:17)
             const float c1 = S_R * dn;                            // y -> scaled residual units

@@ -351,16 +351,18 @@ class StripeComm:
                 imout_local[:h] += from_left
 
     def halo_refresh(self, *arrays: torch.Tensor) -> None:
-        """Owned first rows travel to the LEFT neighbour's halo (X and λ1 after the update)."""
+        """Owned first rows travel to the LEFT neighbour's halo (X and λ1 after the update): all arrays in ONE
+        exchange (stacked into one message per neighbour)."""
         st = self.st
-        if st.world == 1 or st.halo == 0:
+        if st.world == 1 or st.halo == 0 or not arrays:
             return
         h = st.halo
-        for arr in arrays:
-            send = arr[:h] if st.rank > 0 else arr[:0]
-            _, from_right = self._exchange(None, send, arr[:h])
-            if from_right is not None:
-                arr[st.rows_local - h:] = from_right
+        send = torch.stack([arr[:h] for arr in arrays]) if st.rank > 0 else None
+        like = torch.empty((len(arrays), h) + tuple(arrays[0].shape[1:]), dtype=arrays[0].dtype, device=arrays[0].device)
+        _, from_right = self._exchange(None, send if send is not None else like[:0], like)
+        if from_right is not None:
+            for i, arr in enumerate(arrays):
+                arr[st.rows_local - h:] = from_right[i]
 
     def allreduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.st.world > 1:

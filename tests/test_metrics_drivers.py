@@ -108,3 +108,32 @@ def test_dictlearn_host_pieces(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(_lib.LrsError):
             dictlearn.learn_dictionary(torch.zeros(16, 64), 8)
+
+
+def test_mat_reader_reads_all_bundled_files():
+    """matio (v5 via scipy, v7.3 via the in-repo HDF5 reader — no h5py here) on all 14 files of the reference's data/
+    directory: shapes, dtypes and the zero counts of SURVEY §8c (noisy cubes: zeros = mask zeros x 128 bands, which is
+    what makes `blocks_copy == 0` equivalent to the mask, main_LRS_PnP.py:276-278).  Skips without the checkout."""
+    import os
+
+    from oracle import ref_extract as rx
+
+    d = os.path.join(rx.REFERENCE_ROOT, "data")
+    if not os.path.isdir(d):
+        pytest.skip("reference checkout not present")
+    files = sorted(f for f in os.listdir(d) if f.endswith(".mat"))
+    assert len(files) == 14
+    mask_zeros = {"low_rank_sparsity_mask.mat": 66, "second_mask.mat": 300, "third_mask.mat": 330, "fourth_mask.mat": 432}
+    for f, z in mask_zeros.items():
+        msk = np.asarray(matio.loadmat_any(os.path.join(d, f))["msk"])
+        assert msk.shape == (1, 1, 36, 36) and msk.dtype == np.uint8 and int((msk == 0).sum()) == z
+    for tag, (noisy, clean, mask) in drivers.PAIRS.items():
+        cube_n = matio.load_cube(os.path.join(d, noisy))
+        cube_c = matio.load_cube(os.path.join(d, clean))
+        assert cube_n.shape == cube_c.shape == (1, 128, 36, 36) and cube_n.dtype == np.float32
+        Y = matio.unfold_cube(cube_n)
+        assert Y.shape == (1296, 128)
+        assert int((Y == 0).sum()) == mask_zeros[mask] * 128, tag
+        msk = np.asarray(matio.loadmat_any(os.path.join(d, mask))["msk"])
+        assert np.array_equal((Y == 0).all(axis=1), matio.unfold_mask(msk, 128)[:, 0] == 0), tag
+    assert set(files) == {f for p in drivers.PAIRS.values() for f in p}

@@ -57,8 +57,8 @@ class OracleBackend:
         return torch.from_numpy(Xn)
 
 
-def _problem():
-    H, W, B = 10, 9, 14
+def _problem(H=10, W=9):
+    B = 14
     clean, noisy = synth.synthetic_cube(H, W, B, rank=3, seed=5)
     pm = synth.pixel_mask(H, W, "bernoulli", keep=0.65, seed=6)
     Y = synth.observe(noisy, pm)
@@ -68,13 +68,13 @@ def _problem():
     return Y, MtM, D, prm
 
 
-def _worker(rank, world, port, iters, out_dir):
+def _worker(rank, world, port, iters, out_dir, H=10, W=9):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
-        Y, MtM, D, prm = _problem()
+        Y, MtM, D, prm = _problem(H, W)
         st = solver.make_stripe(Y.shape[0], prm.bb, rank, world)
         Yl = torch.from_numpy(Y[st.row_slice].copy())
         Ml = torch.from_numpy(MtM[st.row_slice].copy())
@@ -115,6 +115,26 @@ def test_sharded_equals_unsharded(world, tmp_path):
     err = np.linalg.norm(X - ref.X) / np.linalg.norm(ref.X)
     assert err < 2e-5, err
     assert np.linalg.norm(l1 - ref.lambda_1) / np.linalg.norm(ref.lambda_1) < 1e-4
+
+
+def test_stripes_as_narrow_as_the_halo(tmp_path):
+    """Boundary of the neighbour-only halo exchange: 14 patch rows over 2 ranks = 7 per stripe = bb-1, the narrowest
+    stripe whose halo lies entirely inside the immediate neighbour's owned rows.  One row fewer must be refused."""
+    iters, world, H, W = 2, 2, 3, 7                      # R = 21 unfolded rows
+    mp.spawn(_worker, args=(world, _free_port(), iters, str(tmp_path), H, W), nprocs=world, join=True)
+    Y, MtM, D, prm = _problem(H, W)
+    oprm = orc.Params(gamma=prm.gamma, mu_1=prm.mu_1, mu_2=prm.mu_2, lambda_ista=prm.lambda_ista, Nit=prm.Nit, bb=prm.bb,
+                      slidingDis=prm.slidingDis, step=prm.step)
+    ref = orc.run(Y, MtM, D, oprm, iteration_num=iters)
+    X = np.zeros_like(Y)
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        X[int(z["a"]):int(z["a"]) + z["X"].shape[0]] = z["X"]
+    assert np.linalg.norm(X - ref.X) / np.linalg.norm(ref.X) < 2e-5
+    with pytest.raises(ValueError, match="narrower than the halo"):
+        solver.make_stripe(20, 8, 0, 2)                  # 13 patch rows -> stripes of 6 and 7
+    with pytest.raises(ValueError, match="narrower than the halo"):
+        solver.make_stripe(90, 8, 1, 12)
 
 
 def test_unsharded_driver_with_oracle_backend_matches_oracle_run():
