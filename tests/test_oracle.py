@@ -203,3 +203,38 @@ def test_nlm_restatement_properties():
     assert np.allclose(orc.nlm_column(np.full(20, 2.5), 3, 3, 0.1), 2.5)
     big = orc.nlm_column(x, 3, 3, 1e6)
     assert abs(big[10] - x[7:14].mean()) < 1e-6
+
+
+def test_literal_loop_port_matches_reference_and_oracle():
+    """oracle/literal_loop.py (the per-patch B0 baseline of bench.py) against the vectorised oracle, and — when the
+    checkout is present — against the reference's own ista / delete_element executed literally."""
+    from oracle import literal_loop as ll, ref_extract as rx
+
+    rng = np.random.default_rng(2)
+    n, K, P = 36, 50, 7
+    D = rng.standard_normal((n, K)).astype(np.float32)
+    D /= np.linalg.norm(D, axis=0, keepdims=True)
+    blocks = rng.standard_normal((n, P)).astype(np.float32)
+    mask = rng.random((n, P)) < 0.7
+    mask[:, 2] = True
+    bc = np.where(mask, blocks + 3.0, 0).astype(np.float32)
+    for step in ("spectral", "frob4"):
+        phi, dt = ll.sparse_step_literal(blocks, bc, D, 0.1, 30, step)
+        a = orc.step_constants_batched(D, mask, step)
+        want = D @ orc.ista_soft_batched(blocks, mask, D, a, 0.1, 30)
+        assert rel(phi, want) < 2e-5 and dt > 0
+        sub, _ = ll.sparse_step_literal(blocks, bc, D, 0.1, 30, step, patches=np.array([5, 1]))
+        assert np.array_equal(sub, phi[:, [5, 1]])
+    if rx.reference_available():
+        import torch
+
+        ns = rx.extract("main_LRS_PnP.py")
+        ns["denoise_nl_means"] = rx.soft_shim(10.0)
+        phi, _ = ll.sparse_step_literal(blocks, bc, D, 0.1, 30, "spectral")
+        for jj in range(P):
+            miss = np.where(bc[:, jj] == 0)[0]
+            y, H = torch.tensor(blocks[:, jj]).view(-1, 1), torch.tensor(D)
+            if len(miss):
+                y, H = ns["delete_element"](y, miss.tolist()), ns["delete_element"](H, miss.tolist())
+            lit = torch.mm(torch.tensor(D), ns["ista"](y, H, 0.1, 0, 30)).flatten().numpy()
+            assert rel(phi[:, jj], lit) < 1e-5, jj
