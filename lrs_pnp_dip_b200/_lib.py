@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblrs_pnp.so")
+# LRS_PNP_LIB: developer switch for A/B runs of kernel variants (scripts/ab_fused.py); unset in normal use
+LIB_PATH = os.environ.get("LRS_PNP_LIB") or os.path.join(_HERE, "csrc", "liblrs_pnp.so")
 
 STEP_SPECTRAL, STEP_FROB4 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2

@@ -55,6 +55,15 @@ constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
 #define LRS_WG0_REGS 88
 #define LRS_EPI_REGS 208
 #endif
+#ifndef LRS_B1_EARLY
+#define LRS_B1_EARLY 0       // k-steps of GEMM-B's second atom half issued during the residual phase (see the MMA issuer)
+#endif
+#ifndef LRS_MASK_FOLD
+#define LRS_MASK_FOLD 0      // 1: band-replicated masks folded into the residual constants (no per-element selects)
+#endif
+#ifndef LRS_SOFT_SAT
+#define LRS_SOFT_SAT 0       // 1: soft threshold through fma.sat on the FMA pipe instead of min/max on the ALU pipe
+#endif
 #define LRS_STR2(x) #x
 #define LRS_STR(x) LRS_STR2(x)
 static_assert(128 * LRS_WG0_REGS + 256 * LRS_EPI_REGS <= 384 * 168, "register budget of one CTA per SM");
@@ -170,6 +179,20 @@ __device__ __forceinline__ void soft_pair(float g0, float g1, float T, float& x0
     const float t0 = fminf(fmaxf(g0, -T), T), t1 = fminf(fmaxf(g1, -T), T);
     upk2(sub2(pk2(g0, g1), pk2(t0, t1)), x0, x1);
 }
+// The same through the FMA pipe: clamp(g, -T, T) = (sat(g / 2T + 1/2) - 1/2) 2T, so soft(g, T) = (g + T) - 2T sat(g / 2T + 1/2).
+// The min/max form runs on the half-rate ALU pipe that bounds the epilogue; this one is two FFMA.SAT, one FADD2 and one
+// FFMA2 per pair.  Inside the dead zone the result is a rounding residue of order 2^-24 T instead of an exact zero.
+struct SoftSat {
+    float inv2T;
+    uint64_t T2, m2T2;
+    __device__ __forceinline__ explicit SoftSat(float T) : inv2T(T > 0.f ? 0.5f / T : 0.f), T2(pk2(T, T)), m2T2(pk2(-2.f * T, -2.f * T)) {}
+    __device__ __forceinline__ void operator()(float g0, float g1, float& x0, float& x1) const {
+        float s0, s1;
+        asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(s0) : "f"(g0), "f"(inv2T));
+        asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(s1) : "f"(g1), "f"(inv2T));
+        upk2(fma2(pk2(s0, s1), m2T2, add2(pk2(g0, g1), T2)), x0, x1);
+    }
+};
 
 template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t a, uint32_t* r) {
     if constexpr (N == 8) tmem_ld8(a, r);
@@ -266,7 +289,9 @@ __host__ __device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, 
 }
 
 // KATOMS in {64, 128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
-template <bool DBG, int KATOMS>
+// FOLD: the masks are band-replicated (the a_table step-constant mode, whose table is indexed by the validity of the 8 window
+// rows): the mask is folded into the residual constants, see the residual phase.
+template <bool DBG, int KATOMS, bool FOLD>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm, TilePlan plan) {
     constexpr int NCHUNK = KATOMS / 64;
     constexpr int KH = KATOMS / 2;                    // atoms per GEMM-B half (MMA N)
@@ -365,29 +390,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 {
                     const uint32_t idescB128 = make_idesc_f16(128, KH, /*b_mn_major=*/true);
                     const uint64_t descR0 = make_smem_desc(smem_u32(Rsm), /*lbo=*/R_SK, /*sbo=*/R_SM);
+                    // Issue order of the 8 (atom half, k-step) groups of 3 MMAs.  Half 0 takes every k-step as soon as its
+                    // residual quarter is staged (its completion releases the first soft-threshold chunks); LRS_B1_EARLY
+                    // k-steps of half 1 are slotted into the tensor-pipe gaps of the residual phase instead of all
+                    // running between bar_B[0] and the first GEMM-A chunk.
+                    constexpr int NE = LRS_B1_EARLY;
+                    static_assert(NE >= 0 && NE <= 3, "LRS_B1_EARLY");
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            if (half == 0) {
-                                long long w0 = TSTAMP();
-                                mbar_wait(&sh.bar_R[ks], par);
-                                if (DBG) dbg[1 + ks] += clock64() - w0;
-                                tc_fence_after();
-                            }
-                            const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
-                            const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
-                            const uint64_t r1 = descR0 + (uint64_t)((2 * ks * R_SK) >> 4);
-                            const uint64_t r2 = descR0 + (uint64_t)((R_PIECE + 2 * ks * R_SK) >> 4);
-                            const uint32_t acc = tbase + COL_ALPHA + KH * half;
-                            if (leader) {
-                                mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && ks == 0));
-                                mma_f16_ss(acc, r2, d1, idescB128, true);
-                                mma_f16_ss(acc, r1, d2, idescB128, true);
-                            }
-                            __syncwarp();
+                    for (int step = 0; step < 8; ++step) {
+                        // schedule: h0k0, [h1k0 .. h1k(NE-1) interleaved after h0k0 .. h0k(NE-1)], rest of half 0, rest of half 1
+                        int half, ks;
+                        if (step < 2 * NE) { half = step & 1; ks = step >> 1; }
+                        else if (step < 4 + NE) { half = 0; ks = step - NE; }
+                        else { half = 1; ks = step - 4; }
+                        if (half == 0) {
+                            long long w0 = TSTAMP();
+                            mbar_wait(&sh.bar_R[ks], par);
+                            if (DBG) dbg[1 + ks] += clock64() - w0;
+                            tc_fence_after();
                         }
-                        if (leader) mma_commit(&sh.bar_B[half]);
+                        const uint64_t d1 = descB0 + (uint64_t)(((0 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
+                        const uint64_t d2 = descB0 + (uint64_t)(((1 * 8 + 2 * ks) * D_SI + half * (KH / 8) * D_SK) >> 4);
+                        const uint64_t r1 = descR0 + (uint64_t)((2 * ks * R_SK) >> 4);
+                        const uint64_t r2 = descR0 + (uint64_t)((R_PIECE + 2 * ks * R_SK) >> 4);
+                        const uint32_t acc = tbase + COL_ALPHA + KH * half;
+                        if (leader) {
+                            mma_f16_ss(acc, r1, d1, idescB128, !(it == 0 && ks == 0));
+                            mma_f16_ss(acc, r2, d1, idescB128, true);
+                            mma_f16_ss(acc, r1, d2, idescB128, true);
+                        }
+                        __syncwarp();
+                        if (step == 3 + NE && leader) mma_commit(&sh.bar_B[0]);     // last group of half 0
+                        if (step == 7 && leader) mma_commit(&sh.bar_B[1]);
                         __syncwarp();
                     }
                 }
@@ -486,8 +520,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             const float c1 = S_R * dn;                            // y -> scaled residual units
             const float c2 = inv_a * S_R / (S_ALPHA * S_D);       // acc (= S_ALPHA S_D a D alpha') -> scaled residual units
 #pragma unroll
-            for (int c = 0; c < CW; ++c) ysc[c] *= c1;
+            for (int c = 0; c < CW; ++c) ysc[c] = ((mbits >> c) & 1u) ? ysc[c] * c1 : 0.f;    // y' stored masked
             const uint64_t nc2 = pk2(-c2, -c2);
+            // slot c holds window row c % 8 (see above): with a band-replicated mask bit c % 8 speaks for slot c
+            uint64_t nc2m[NPX / 2];
+#pragma unroll
+            for (int c = 0; c < NPX / 2; ++c)
+                nc2m[c] = pk2(((mbits >> (2 * c)) & 1u) ? -c2 : 0.f, ((mbits >> (2 * c + 1)) & 1u) ? -c2 : 0.f);
+            const SoftSat softsat(Tn);
             if (DBG) ed[7] += clock64() - tp0;
 
             for (int it = 0; it < Nit; ++it, ++gi) {
@@ -500,43 +540,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     if (DBG) ed[1] += clock64() - tr0;
                     tc_fence_after();
                 }
+                // FOLD: band-replicated masks (validity depends on the window row only), so the mask is folded into four
+                // packed constants nc2m[row pair] = -c2 .* m and into y' itself: r = y'm - (c2 m) Da needs no per-element
+                // select (the selects run on the half-rate ALU pipe that bounds the epilogue).
+                {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {             // pixel quarter = GEMM-B k-step; my NPX pixels of it
-                    uint32_t p1[NPX / 2], p2[NPX / 2];
-                    if (it > 0) {
-                        uint32_t b0[NPX], b1[NPX];
-                        tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
-                        tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
-                        tmem_wait_ld();
+                    for (int ks = 0; ks < 4; ++ks) {             // pixel quarter = GEMM-B k-step; my NPX pixels of it
+                        uint32_t p1[NPX / 2], p2[NPX / 2];
+                        if (it > 0) {
+                            uint32_t b0[NPX], b1[NPX];
+                            tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
+                            tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < NPX / 2; ++c) {
-                            const int e = NPX * ks + 2 * c;
-                            const uint64_t sm2 = add2(pk2(__uint_as_float(b0[2 * c]), __uint_as_float(b0[2 * c + 1])),
-                                                      pk2(__uint_as_float(b1[2 * c]), __uint_as_float(b1[2 * c + 1])));
-                            float r0, r1;
-                            upk2(fma2(nc2, sm2, pk2(ysc[e], ysc[e + 1])), r0, r1);
-                            r0 = ((mbits >> e) & 1u) ? r0 : 0.f;
-                            r1 = ((mbits >> (e + 1)) & 1u) ? r1 : 0.f;
-                            split_pair(r0, r1, p1[c], p2[c]);
+                            for (int c = 0; c < NPX / 2; ++c) {
+                                const int e = NPX * ks + 2 * c;
+                                const uint64_t sm2 = add2(pk2(__uint_as_float(b0[2 * c]), __uint_as_float(b0[2 * c + 1])),
+                                                          pk2(__uint_as_float(b1[2 * c]), __uint_as_float(b1[2 * c + 1])));
+                                float r0, r1;
+                                upk2(fma2(FOLD ? nc2m[c] : nc2, sm2, pk2(ysc[e], ysc[e + 1])), r0, r1);
+                                if (!FOLD) {
+                                    r0 = ((mbits >> e) & 1u) ? r0 : 0.f;
+                                    r1 = ((mbits >> (e + 1)) & 1u) ? r1 : 0.f;
+                                }
+                                split_pair(r0, r1, p1[c], p2[c]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NPX / 2; ++c) {
+                                const int e = NPX * ks + 2 * c;
+                                split_pair(ysc[e], ysc[e + 1], p1[c], p2[c]);   // y' is stored masked
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < NPX / 2; ++c) {
-                            const int e = NPX * ks + 2 * c;
-                            float r0 = ((mbits >> e) & 1u) ? ysc[e] : 0.f;
-                            float r1 = ((mbits >> (e + 1)) & 1u) ? ysc[e + 1] : 0.f;
-                            split_pair(r0, r1, p1[c], p2[c]);
-                        }
+                        // my 8 pixels = k-group 2ks + cg of my row m: one 16-byte store per piece (a warp covers 512 contiguous
+                        // bytes per store: conflict-free), then publish to the async proxy
+                        uint8_t* rrow = Rsm + (uint32_t)(m >> 3) * R_SM + (uint32_t)(m & 7) * 16 + (uint32_t)(NCG * ks + cg) * R_SK;
+                        *reinterpret_cast<uint4*>(rrow) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                        *reinterpret_cast<uint4*>(rrow + R_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                        fence_async_smem();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sh.bar_R[ks]);
                     }
-                    // my 8 pixels = k-group 2ks + cg of my row m: one 16-byte store per piece (a warp covers 512 contiguous
-                    // bytes per store: conflict-free), then publish to the async proxy
-                    uint8_t* rrow = Rsm + (uint32_t)(m >> 3) * R_SM + (uint32_t)(m & 7) * 16 + (uint32_t)(NCG * ks + cg) * R_SK;
-                    *reinterpret_cast<uint4*>(rrow) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                    *reinterpret_cast<uint4*>(rrow + R_PIECE) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-                    fence_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.bar_R[ks]);
                 }
                 // ---- soft threshold, 4 chunks of 64 atoms; my CW columns of each.  The load of chunk j+1 is in
                 //      flight while chunk j is processed. ----
@@ -563,7 +608,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 #pragma unroll
                     for (int c = 0; c < CW / 2; ++c) {
                         float x0, x1;
-                        soft_pair(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), Tn, x0, x1);
+                        if (LRS_SOFT_SAT) softsat(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), x0, x1);
+                        else soft_pair(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), Tn, x0, x1);
                         g[2 * c] = __float_as_uint(x0);
                         g[2 * c + 1] = __float_as_uint(x1);
                         split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
@@ -701,11 +747,13 @@ template <int K>
 static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
+    const bool fold = LRS_MASK_FOLD && prm.a_table != nullptr && prm.a_patch == nullptr;
 #ifdef LRS_DIAGNOSTICS   // liblrs_pnp_diag.so only: barrier-wait counters (include/lrs_pnp_diag.h)
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
-    auto kern = dbg ? sparse_fused_tc_kernel<true, K> : sparse_fused_tc_kernel<false, K>;
+    auto kern = dbg ? (fold ? sparse_fused_tc_kernel<true, K, true> : sparse_fused_tc_kernel<true, K, false>)
+                    : (fold ? sparse_fused_tc_kernel<false, K, true> : sparse_fused_tc_kernel<false, K, false>);
 #else
-    auto kern = sparse_fused_tc_kernel<false, K>;
+    auto kern = fold ? sparse_fused_tc_kernel<false, K, true> : sparse_fused_tc_kernel<false, K, false>;
 #endif
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
