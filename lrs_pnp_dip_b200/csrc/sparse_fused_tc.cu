@@ -59,10 +59,16 @@ constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
 #define LRS_B1_EARLY 0       // k-steps of GEMM-B's second atom half issued during the residual phase (see the MMA issuer)
 #endif
 #ifndef LRS_MASK_FOLD
-#define LRS_MASK_FOLD 0      // 1: band-replicated masks folded into the residual constants (no per-element selects)
+#define LRS_MASK_FOLD 1      // 1: band-replicated masks folded into the residual constants (no per-element selects)
+#endif
+#ifndef LRS_TAIL_SPLIT
+#define LRS_TAIL_SPLIT 1     // 1: the last soft-threshold chunk is released to GEMM-A in two 16-atom halves per column group
+#endif
+#ifndef LRS_SPLIT_FHFMA
+#define LRS_SPLIT_FHFMA 1    // 1: low fp16 piece through the mixed-precision FMA (FHFMA)
 #endif
 #ifndef LRS_SOFT_SAT
-#define LRS_SOFT_SAT 0       // 1: soft threshold through fma.sat on the FMA pipe instead of min/max on the ALU pipe
+#define LRS_SOFT_SAT 0       // 1 / 2: soft threshold through fma.sat on the FMA pipe (see SoftSat; both measured, neither adopted)
 #endif
 #define LRS_STR2(x) #x
 #define LRS_STR(x) LRS_STR2(x)
@@ -92,27 +98,6 @@ static_assert(B_SS, "the TMEM-operand GEMM-B variant (v2) was removed with the s
 // residual pieces in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048 + piece*16384
 constexpr uint32_t R_SMEM_BYTES = B_SS ? 32 * 1024 : 0;
 constexpr uint32_t R_SK = 2048, R_SM = 128, R_PIECE = 16 * 1024;
-// GEMM-A variant: the second state piece (a2) as the A operand from SHARED memory (an N = 64 MMA costs 60 cycles with A in
-// shared memory, 88 with A in TMEM).  With a2 out of TMEM the four a1 chunks (32 columns each) fit the 128 staging
-// columns side by side, so the staging double-buffer hazard (and its barrier waits) disappears.  Requires B_SS.
-#ifdef LRS_A2_SS
-constexpr bool A2_SS = true;
-#else
-constexpr bool A2_SS = false;
-#endif
-// A2_SS measured on B200: 690 ms vs 655 ms (cfg 4) — the extra shared-memory reads contend with B's
-static_assert(!A2_SS || B_SS, "A2_SS uses staging buffer 0 for a1 chunks: the residual pieces must live in shared memory");
-// a2 in shared memory, K-major A operand (bytes): (k%8)*2 + (m%8)*16 + (m/8)*128 + (k/8)*2048     (k = atom 0..255)
-// experiment: the first state piece from shared memory as well, so that every MMA of the kernel is an SS form
-#ifdef LRS_A1_SS
-constexpr bool A1_SS = true;
-#else
-constexpr bool A1_SS = false;
-#endif
-static_assert(!A1_SS || A2_SS, "A1_SS extends A2_SS");
-constexpr uint32_t A2_SMEM_BYTES = (A2_SS ? 64 * 1024 : 0) + (A1_SS ? 64 * 1024 : 0);
-constexpr uint32_t A1_OFF = 64 * 1024;   // a1 pieces follow the a2 pieces, same layout
-constexpr uint32_t A2_SK = 2048, A2_SM = 128;
 constexpr uint32_t D_SK = 2048, D_SI = 128;
 // Next tile's patch values, gathered by the otherwise idle warps 1..3 while the current tile iterates:
 // V = X + L/mu as [pixel][patch] floats (32 KB) and the observed flags as [pixel][patch] bytes (8 KB)
@@ -124,6 +109,7 @@ struct __align__(8) Shared {
     uint64_t bar_B[2];        // MMA -> epilogue: GEMM-B complete for atom half h (h = 0 only when !B_SS)      (commit)
     uint64_t bar_S[MAXCHUNK];   // epilogue -> MMA: soft-thresholded state pieces of chunk j are staged     (16 warps)
     uint64_t bar_A[MAXCHUNK];   // MMA -> epilogue: GEMM-A of chunk j complete (staging free / Da final)    (commit)
+    uint64_t bar_T[2];        // epilogue -> MMA: first / second 16-atom halves of the LAST chunk are staged (NEPI warps)
     uint64_t bar_G_full;      // loader -> epilogue: the gathered values of the next tile are in shared memory (loader warps)
     uint64_t bar_G_free;      // epilogue -> loader: the gather buffer has been consumed                      (NEPI warps)
     uint32_t tmem_base;
@@ -166,9 +152,18 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 // x (already scaled) -> two fp16 pieces, two values per 32-bit word
 __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p1, uint32_t& p2) {
     __half2 h = __floats2half2_rn(x0, x1);
-    float2 f = __half22float2(h);
     float l0, l1;
+#if LRS_SPLIT_FHFMA
+    // x - fp16(x) with the mixed-precision FMA of sm_100 (fma.rn.f32.f16 -> FHFMA): one instruction per element instead of
+    // a conversion and half a packed subtract; the difference is exact either way
+    const unsigned short hl = __half_as_ushort(__low2half(h)), hh = __half_as_ushort(__high2half(h));
+    const unsigned short m1 = 0xBC00;   // -1.0 in fp16
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l0) : "h"(hl), "h"(m1), "f"(x0));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l1) : "h"(hh), "h"(m1), "f"(x1));
+#else
+    float2 f = __half22float2(h);
     upk2(sub2(pk2(x0, x1), pk2(f.x, f.y)), l0, l1);
+#endif
     __half2 l = __floats2half2_rn(l0, l1);
     p1 = pack_h2(h);
     p2 = pack_h2(l);
@@ -179,10 +174,31 @@ __device__ __forceinline__ void soft_pair(float g0, float g1, float T, float& x0
     const float t0 = fminf(fmaxf(g0, -T), T), t1 = fminf(fmaxf(g1, -T), T);
     upk2(sub2(pk2(g0, g1), pk2(t0, t1)), x0, x1);
 }
-// The same through the FMA pipe: clamp(g, -T, T) = (sat(g / 2T + 1/2) - 1/2) 2T, so soft(g, T) = (g + T) - 2T sat(g / 2T + 1/2).
-// The min/max form runs on the half-rate ALU pipe that bounds the epilogue; this one is two FFMA.SAT, one FADD2 and one
-// FFMA2 per pair.  Inside the dead zone the result is a rounding residue of order 2^-24 T instead of an exact zero.
+// The same through the FMA pipe (the min/max form runs on the half-rate ALU pipe that bounds the epilogue).
+//   LRS_SOFT_SAT = 2 (exact): with s = 2^-40, sat(g s - T s) = max(g - T, 0) s and sat(-g s - T s) = max(-g - T, 0) s — one
+//     rounding of g -/+ T each, as in sign(g) max(|g| - T, 0) (scaling by a power of two commutes with the rounding; |g| < 2^40
+//     is far beyond what the fp16 pieces can carry) — so soft(g, T) = (pos - neg) 2^40 bit for bit, exact zeros included:
+//     four FFMA.SAT, one FADD2 and one FMUL2 per pair.
+//   LRS_SOFT_SAT = 1 (inexact in the dead zone): clamp(g, -T, T) = (sat(g / 2T + 1/2) - 1/2) 2T, soft = (g + T) - 2T sat(..):
+//     two FFMA.SAT, one FADD2, one FFMA2 per pair, but |g| < T leaves a residue of order 2^-24 T instead of an exact zero
+//     (an all-zero solution comes back as noise) — measured only 0.2 % faster than the exact min/max form; kept for the record.
 struct SoftSat {
+#if LRS_SOFT_SAT == 2
+    float s, nTs;
+    uint64_t up2;
+    __device__ __forceinline__ explicit SoftSat(float T) : s(9.094947017729282e-13f), nTs(-T * 9.094947017729282e-13f),
+                                                          up2(pk2(1099511627776.0f, 1099511627776.0f)) {}
+    __device__ __forceinline__ void operator()(float g0, float g1, float& x0, float& x1) const {
+        float p0, p1, n0, n1;
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(p0) : "f"(g0), "f"(s), "f"(nTs));
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(p1) : "f"(g1), "f"(s), "f"(nTs));
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(n0) : "f"(g0), "f"(-s), "f"(nTs));
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(n1) : "f"(g1), "f"(-s), "f"(nTs));
+        uint64_t d = sub2(pk2(p0, p1), pk2(n0, n1)), r;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(d), "l"(up2));
+        upk2(r, x0, x1);
+    }
+#else
     float inv2T;
     uint64_t T2, m2T2;
     __device__ __forceinline__ explicit SoftSat(float T) : inv2T(T > 0.f ? 0.5f / T : 0.f), T2(pk2(T, T)), m2T2(pk2(-2.f * T, -2.f * T)) {}
@@ -192,6 +208,7 @@ struct SoftSat {
         asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(s1) : "f"(g1), "f"(inv2T));
         upk2(fma2(pk2(s0, s1), m2T2, add2(pk2(g0, g1), T2)), x0, x1);
     }
+#endif
 };
 
 template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t a, uint32_t* r) {
@@ -300,10 +317,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* Dsm = smem;
     uint8_t* Rsm = smem + D_SMEM_BYTES;
-    uint8_t* A2sm = smem + D_SMEM_BYTES + R_SMEM_BYTES;
-    float* Gv = reinterpret_cast<float*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES);
-    uint8_t* Gok = smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + 64 * TILE * 4;
-    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES);
+    float* Gv = reinterpret_cast<float*>(smem + D_SMEM_BYTES + R_SMEM_BYTES);
+    uint8_t* Gok = smem + D_SMEM_BYTES + R_SMEM_BYTES + 64 * TILE * 4;
+    Shared& sh = *reinterpret_cast<Shared*>(smem + D_SMEM_BYTES + R_SMEM_BYTES + G_SMEM_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t total = prm.p_end - prm.p_begin;
@@ -352,6 +368,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             mbar_init(&sh.bar_S[j], NEPI);
             mbar_init(&sh.bar_A[j], 1);
         }
+        mbar_init(&sh.bar_T[0], NEPI);
+        mbar_init(&sh.bar_T[1], NEPI);
         mbar_init(&sh.bar_G_full, FIRST_EPI - 1);
         mbar_init(&sh.bar_G_free, NEPI);
         mbar_fence_init();
@@ -428,26 +446,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 // ---- GEMM-A: Da = state D^T, chunk by chunk as the soft-threshold epilogue releases them ----
 #pragma unroll
                 for (int j = 0; j < NCHUNK; ++j) {
+                    const uint32_t stg = tbase + ((j & 1) ? COL_STG1 : COL_STG0);
+                    // TAIL: the last chunk is released in two halves (k-steps {0,2}, then {1,3}: each column group stages its
+                    // first 16 atoms, then its last 16), so only two k-steps of MMAs remain after the soft threshold ends
+                    constexpr bool TAIL = LRS_TAIL_SPLIT != 0;
+                    if (TAIL && j == NCHUNK - 1) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            long long w1 = TSTAMP();
+                            mbar_wait(&sh.bar_T[h], par);
+                            if (DBG) dbg[5 + j] += clock64() - w1;
+                            tc_fence_after();
+#pragma unroll
+                            for (int ks = h; ks < 4; ks += 2) {
+                                const uint64_t d = descA0 + (uint64_t)(((8 * j + 2 * ks) * D_SK) >> 4);
+                                if (leader) {
+                                    mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));   // a1 [D1;D2]
+                                    mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);                // a2 D1
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (leader) mma_commit(&sh.bar_A[j]);
+                        __syncwarp();
+                        continue;
+                    }
                     long long w1 = TSTAMP();
                     mbar_wait(&sh.bar_S[j], par);
                     if (DBG) dbg[5 + j] += clock64() - w1;
                     tc_fence_after();
-                    const uint32_t stg = tbase + (A2_SS ? COL_STG0 + 32 * j : ((j & 1) ? COL_STG1 : COL_STG0));
-                    const uint64_t descA2 = make_smem_desc(smem_u32(A2sm), /*lbo=*/A2_SK, /*sbo=*/A2_SM);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint64_t d = descA0 + (uint64_t)(((8 * j + 2 * ks) * D_SK) >> 4);
-                        const uint64_t a2 = descA2 + (uint64_t)(((8 * j + 2 * ks) * A2_SK) >> 4);
                         if (leader) {
-                            if (A1_SS) mma_f16_ss(tbase + COL_ACC, a2 + (uint64_t)(A1_OFF >> 4), d, idescA128, !(j == 0 && ks == 0));
-                            else mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));  // a1 [D1;D2]
-                            if (A2_SS) mma_f16_ss(tbase + COL_ACC, a2, d, idescA64, true);                   // a2 D1 (A from smem)
-                            else mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);          // a2 D1
+                            mma_f16_ts(tbase + COL_ACC, stg + 8 * ks, d, idescA128, !(j == 0 && ks == 0));  // a1 [D1;D2]
+                            mma_f16_ts(tbase + COL_ACC, stg + 32 + 8 * ks, d, idescA64, true);               // a2 D1
                         }
                     }
                     // staging-release commits are only needed when chunks share staging buffers; the last chunk always
                     // signals "Da complete"
-                    if ((j == NCHUNK - 1 || (!A2_SS && j + 2 < NCHUNK)) && leader) mma_commit(&sh.bar_A[j]);
+                    if ((j == NCHUNK - 1 || j + 2 < NCHUNK) && leader) mma_commit(&sh.bar_A[j]);
                     __syncwarp();
                 }
                 if (DBG) dbg[10] += 1;
@@ -605,46 +643,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                     }
                     tmem_wait_ld();
                     if (j + 1 < NCHUNK && !(B_SS && j + 1 == FIRST_B1_CHUNK)) tmem_ldN<CW>(lane_addr + col + 64, gn);
+                    const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
+                    auto soft_pairs = [&](int c_lo, int c_hi) {
 #pragma unroll
-                    for (int c = 0; c < CW / 2; ++c) {
-                        float x0, x1;
-                        if (LRS_SOFT_SAT) softsat(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), x0, x1);
-                        else soft_pair(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), Tn, x0, x1);
-                        g[2 * c] = __float_as_uint(x0);
-                        g[2 * c + 1] = __float_as_uint(x1);
-                        split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
-                    }
-                    if (!A2_SS && j >= 2) {  // staging buffer (j&1) is free once GEMM-A of chunk j-2 has completed
-                        const long long tw = TSTAMP();
-                        mbar_wait(&sh.bar_A[j - 2], par);
-                        if (DBG) ed[3 + (j - 2)] += clock64() - tw;
-                        tc_fence_after();
-                    }
-                    tmem_stN<CW>(lane_addr + col, g);
-                    if (A2_SS) {
-                        if (!A1_SS) tmem_stN<CW / 2>(lane_addr + COL_STG0 + 32 * j + (CW / 2) * cg, p1);
-                        // my CW atoms = CW/8 k-groups of row m: one 16-byte store each (conflict-free: a warp covers 512
-                        // contiguous bytes), then publish to the async proxy
-                        uint8_t* arow = A2sm + (uint32_t)(m >> 3) * A2_SM + (uint32_t)(m & 7) * 16 +
-                                        (uint32_t)(8 * j + (CW / 8) * cg) * A2_SK;
-#pragma unroll
-                        for (int gk = 0; gk < CW / 8; ++gk)
-                            *reinterpret_cast<uint4*>(arow + gk * A2_SK) = make_uint4(p2[4 * gk], p2[4 * gk + 1], p2[4 * gk + 2], p2[4 * gk + 3]);
-                        if (A1_SS) {
-#pragma unroll
-                            for (int gk = 0; gk < CW / 8; ++gk)
-                                *reinterpret_cast<uint4*>(arow + A1_OFF + gk * A2_SK) = make_uint4(p1[4 * gk], p1[4 * gk + 1], p1[4 * gk + 2], p1[4 * gk + 3]);
+                        for (int c = c_lo; c < c_hi; ++c) {
+                            float x0, x1;
+                            if (LRS_SOFT_SAT) softsat(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), x0, x1);
+                            else soft_pair(__uint_as_float(g[2 * c]), __uint_as_float(g[2 * c + 1]), Tn, x0, x1);
+                            g[2 * c] = __float_as_uint(x0);
+                            g[2 * c + 1] = __float_as_uint(x1);
+                            split_pair(x0 * S_ALPHA, x1 * S_ALPHA, p1[c], p2[c]);
                         }
-                        fence_async_smem();
+                    };
+                    auto wait_staging = [&]() {
+                        if (j >= 2) {  // staging buffer (j&1) is free once GEMM-A of chunk j-2 has completed
+                            const long long tw = TSTAMP();
+                            mbar_wait(&sh.bar_A[j - 2], par);
+                            if (DBG) ed[3 + (j - 2)] += clock64() - tw;
+                            tc_fence_after();
+                        }
+                    };
+                    if (LRS_TAIL_SPLIT && j == NCHUNK - 1) {
+                        // last chunk: my first 16 atoms (k-step 2 cg), then my last 16 (k-step 2 cg + 1), each released on its
+                        // own barrier, so that only two k-steps of GEMM-A remain when the soft threshold ends
+                        static_assert(CW == 32, "the tail split stages 16-atom halves with x16 / x8 TMEM stores");
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            soft_pairs(8 * h, 8 * h + 8);
+                            if (h == 0) wait_staging();
+                            tmem_st16(lane_addr + col + 16 * h, g + 16 * h);
+                            tmem_st8(lane_addr + stg + (CW / 2) * cg + 8 * h, p1 + 8 * h);
+                            tmem_st8(lane_addr + stg + 32 + (CW / 2) * cg + 8 * h, p2 + 8 * h);
+                            tmem_wait_st();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sh.bar_T[h]);
+                        }
                     } else {
-                        const uint32_t stg = (j & 1) ? COL_STG1 : COL_STG0;
+                        soft_pairs(0, CW / 2);
+                        wait_staging();
+                        tmem_stN<CW>(lane_addr + col, g);
                         tmem_stN<CW / 2>(lane_addr + stg + (CW / 2) * cg, p1);
                         tmem_stN<CW / 2>(lane_addr + stg + 32 + (CW / 2) * cg, p2);
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sh.bar_S[j]);
                     }
-                    tmem_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.bar_S[j]);
                 }
                 if (DBG) ed[6] += clock64() - ts0;
             }
@@ -746,7 +791,7 @@ static TilePlan make_tile_plan(const FusedParams& prm, int sms) {
 template <int K>
 static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
-    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + A2_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
+    const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
     const bool fold = LRS_MASK_FOLD && prm.a_table != nullptr && prm.a_patch == nullptr;
 #ifdef LRS_DIAGNOSTICS   // liblrs_pnp_diag.so only: barrier-wait counters (include/lrs_pnp_diag.h)
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
