@@ -67,6 +67,12 @@ constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
 #ifndef LRS_SPLIT_FHFMA
 #define LRS_SPLIT_FHFMA 1    // 1: low fp16 piece through the mixed-precision FMA (FHFMA)
 #endif
+#ifndef LRS_RES_PREFETCH
+#define LRS_RES_PREFETCH 0   // 1: residual phase requests the next quarter's accumulators one quarter ahead
+#endif
+#ifndef LRS_DEFER_ARRIVE
+#define LRS_DEFER_ARRIVE 1   // 1: soft chunk j is signalled from the middle of chunk j+1 (hides the TMEM store latency)
+#endif
 #ifndef LRS_SOFT_SAT
 #define LRS_SOFT_SAT 0       // 1 / 2: soft threshold through fma.sat on the FMA pipe (see SoftSat; both measured, neither adopted)
 #endif
@@ -582,14 +588,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                 // packed constants nc2m[row pair] = -c2 .* m and into y' itself: r = y'm - (c2 m) Da needs no per-element
                 // select (the selects run on the half-rate ALU pipe that bounds the epilogue).
                 {
+                    // LRS_RES_PREFETCH: the accumulators of quarter ks+1 are requested before quarter ks is processed
+                    uint32_t ba[2][NPX], bb[2][NPX];
+                    if (LRS_RES_PREFETCH && it > 0) {
+                        tmem_ld8(lane_addr + COL_ACC + NPX * cg, ba[0]);
+                        tmem_ld8(lane_addr + COL_ACC + 64 + NPX * cg, bb[0]);
+                    }
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {             // pixel quarter = GEMM-B k-step; my NPX pixels of it
                         uint32_t p1[NPX / 2], p2[NPX / 2];
                         if (it > 0) {
-                            uint32_t b0[NPX], b1[NPX];
-                            tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
-                            tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
+                            uint32_t* b0 = ba[LRS_RES_PREFETCH ? (ks & 1) : 0];
+                            uint32_t* b1 = bb[LRS_RES_PREFETCH ? (ks & 1) : 0];
+                            if (!LRS_RES_PREFETCH) {
+                                tmem_ld8(lane_addr + COL_ACC + 16 * ks + NPX * cg, b0);
+                                tmem_ld8(lane_addr + COL_ACC + 64 + 16 * ks + NPX * cg, b1);
+                            }
                             tmem_wait_ld();
+                            if (LRS_RES_PREFETCH && ks < 3) {
+                                tmem_ld8(lane_addr + COL_ACC + 16 * (ks + 1) + NPX * cg, ba[(ks + 1) & 1]);
+                                tmem_ld8(lane_addr + COL_ACC + 64 + 16 * (ks + 1) + NPX * cg, bb[(ks + 1) & 1]);
+                            }
 #pragma unroll
                             for (int c = 0; c < NPX / 2; ++c) {
                                 const int e = NPX * ks + 2 * c;
@@ -663,6 +682,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                             tc_fence_after();
                         }
                     };
+                    // LRS_DEFER_ARRIVE: chunk j's "staged" signal is given in the middle of chunk j+1's arithmetic, when its TMEM
+                    // stores have landed, instead of stalling on tcgen05.wait::st right after issuing them
+                    auto flush_pending = [&]() {
+                        if (LRS_DEFER_ARRIVE && j > 0) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sh.bar_S[j - 1]);
+                        }
+                    };
                     if (LRS_TAIL_SPLIT && j == NCHUNK - 1) {
                         // last chunk: my first 16 atoms (k-step 2 cg), then my last 16 (k-step 2 cg + 1), each released on its
                         // own barrier, so that only two k-steps of GEMM-A remain when the soft threshold ends
@@ -670,7 +699,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             soft_pairs(8 * h, 8 * h + 8);
-                            if (h == 0) wait_staging();
+                            if (h == 0) {
+                                flush_pending();
+                                wait_staging();
+                            }
                             tmem_st16(lane_addr + col + 16 * h, g + 16 * h);
                             tmem_st8(lane_addr + stg + (CW / 2) * cg + 8 * h, p1 + 8 * h);
                             tmem_st8(lane_addr + stg + 32 + (CW / 2) * cg + 8 * h, p2 + 8 * h);
@@ -680,15 +712,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
                             if (lane == 0) mbar_arrive(&sh.bar_T[h]);
                         }
                     } else {
-                        soft_pairs(0, CW / 2);
+                        soft_pairs(0, CW / 4);
+                        flush_pending();
+                        soft_pairs(CW / 4, CW / 2);
                         wait_staging();
                         tmem_stN<CW>(lane_addr + col, g);
                         tmem_stN<CW / 2>(lane_addr + stg + (CW / 2) * cg, p1);
                         tmem_stN<CW / 2>(lane_addr + stg + 32 + (CW / 2) * cg, p2);
-                        tmem_wait_st();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sh.bar_S[j]);
+                        if (!LRS_DEFER_ARRIVE || j == NCHUNK - 1) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sh.bar_S[j]);
+                        }
                     }
                 }
                 if (DBG) ed[6] += clock64() - ts0;
