@@ -72,6 +72,27 @@ def make_inputs(workload):
 CPU_SAMPLE_ROWS = 192      # FIXED sample: the first 192 unfolded rows = 185 patch row starts x ALL column starts
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU legs are meant to use every host core, so the BLAS / OpenMP
+    pools are resized at run time (threadpoolctl) and torch's intra-op pool too.  Returns the thread count in effect."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)
+        got = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+        n_eff = max(got) if got else n
+    except Exception:
+        n_eff = n
+    try:
+        import torch
+
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return int(n_eff)
+
+
 def cpu_sample(Y):
     """The bounded CPU sample of a workload — independent of any time budget, so the figure is reproducible."""
     return np.ascontiguousarray(Y[:min(CPU_SAMPLE_ROWS, Y.shape[0])])
@@ -98,6 +119,7 @@ def cpu_patch_iters_per_s(Y, D, budget_s=15.0):
     """cpu_baseline leg: one untimed pass (thread pools, page faults), then whole passes over the FIXED sample until
     ``budget_s`` is used (at least one); value = patch-iterations / mean pass time."""
     sub = cpu_sample(Y)
+    threads = use_all_host_threads()
     cpu_pass(sub, D)
     times, t_end = [], time.perf_counter() + budget_s
     while True:
@@ -105,7 +127,7 @@ def cpu_patch_iters_per_s(Y, D, budget_s=15.0):
         times.append(dt)
         if time.perf_counter() + dt > t_end:
             break
-    return P_s * NIT / float(np.mean(times)), os.cpu_count() or 1, sample_text(P_s, sub.shape[0], sub.shape[1]), times
+    return P_s * NIT / float(np.mean(times)), threads, sample_text(P_s, sub.shape[0], sub.shape[1]), times
 
 
 def run_reference(args, rank):
@@ -115,6 +137,7 @@ def run_reference(args, rank):
         return
     Y, pm, D = make_inputs(args.workload)
     sub = cpu_sample(Y)
+    threads = use_all_host_threads()
     times, P_s = [], 0
     for i in range(args.warmup + args.steps):
         P_s, dt = cpu_pass(sub, D)
@@ -124,7 +147,7 @@ def run_reference(args, rank):
     val = P_s * NIT / mean
     R, C = Y.shape
     P = (R - BB + 1) * (C - BB + 1)
-    cores = os.cpu_count() or 1
+    cores = threads
     sample = sample_text(P_s, sub.shape[0], C)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * mean, "higher_is_better": True, "scaling": "strong",
@@ -486,6 +509,7 @@ def run_cfg1_reference(args, rank):
     if rank != 0:
         return
     Y, _, D = cfg1_inputs()
+    threads = use_all_host_threads()
     times = []
     for i in range(args.warmup + args.steps):
         P_s, dt = cfg1_cpu_pass(Y, D)
@@ -499,7 +523,7 @@ def run_cfg1_reference(args, rank):
                       "vs_baseline": None, "dtype": "f32", "data": "bundled cube, synthetic dictionary",
                       "config": {"workload": CFG1_NAME, "patches_per_step": P_s, "patches_full_workload": 144, "extrapolated": False,
                                  "full_workload_ms_per_step_extrapolated": 1e3 * 144 * CFG1_NIT / val},
-                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
@@ -584,9 +608,10 @@ def run_cfg1_ours(args):
     achieved = flops / (kms * 1e-3) / 1e12
     cpu = None
     if not args.no_cpu:
+        threads = use_all_host_threads()
         cfg1_cpu_pass(Y, D)
         P_s, dt = cfg1_cpu_pass(Y, D)
-        cpu = {"value": P_s * CFG1_NIT / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": P_s * CFG1_NIT / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{P_s} of the 144 patches x {CFG1_NIT} iterations, literal per-patch loop with one SVD per patch (B0)"}
     print(json.dumps({
         "metric": METRIC, "value": P * CFG1_NIT / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": reps, "warmup": args.warmup,
