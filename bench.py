@@ -48,8 +48,9 @@ def peaks():
 
 
 def ncu_traffic(workload, world):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload (or None)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes of the dominant kernel per step from the COMMITTED ncu capture of the same workload (or None): a stored
+    figure (profiles/r02_traffic.json says how it was taken), not something this run measures."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return json.load(open(p)).get(workload, {}).get(str(world))
     except (OSError, ValueError):
@@ -454,7 +455,9 @@ def run_ours(args, rank, world, local_rank):
                                                    "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload, world), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                         "traffic": ncu_traffic(args.workload, world),
+                         "traffic_unit": "bytes per step = all fused launches of one step (ncu dram read+write)",
+                         "traffic_source": "stored ncu capture profiles/r02_traffic.json (not measured in this run)",
                          "algorithmic_bytes": 3.0 * 4 * R * C / world + 4.0 * 64 * P_local,
                          "kernel": "sparse_fused_tc_kernel, all column-start-range launches of one step (span on the caller's stream, "
                                    "including the overlapped overlap-sum kernels)", "kernel_ms": float(kms.item()),

@@ -137,3 +137,55 @@ def test_mat_reader_reads_all_bundled_files():
         msk = np.asarray(matio.loadmat_any(os.path.join(d, mask))["msk"])
         assert np.array_equal((Y == 0).all(axis=1), matio.unfold_mask(msk, 128)[:, 0] == 0), tag
     assert set(files) == {f for p in drivers.PAIRS.values() for f in p}
+
+
+@pytest.mark.parametrize("kind", ["skip", "1lip"])
+def test_dip_hook_with_the_references_own_networks(kind, golden):
+    """(f)2: the DIP variants keep the reference's networks.  With the checkout present, build them through
+    drivers.reference_net_factory exactly as the scripts do (skip(128,128,[128]*5,...), main_LRS_PnP_DIP_pro.py:215-221;
+    my_Lipschitz_Unet(128,128,ln_lambda=1), main_LRS_PnP_DIP_1-LiP.py:212-214) and run the get_DIP_out restatement
+    (fresh net, masked MSE, Adam, on-device fold/unfold instead of the CPU round trip of :412-419) for a few iterations on
+    the bundled base cube.  CPU here; the same hook runs on CUDA tensors unchanged.  Skips without the checkout."""
+    import sys
+    import types
+
+    from oracle import ref_extract as rx
+
+    if not rx.reference_available():
+        pytest.skip("reference checkout not present")
+    if kind == "1lip" and "matplotlib" not in sys.modules:
+        # my_Lipschitz_Unet.py:12 imports matplotlib (absent here) for a plotting helper the forward pass never touches
+        mpl = types.ModuleType("matplotlib")
+        mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+        sys.modules.setdefault("matplotlib", mpl)
+        sys.modules.setdefault("matplotlib.pyplot", mpl.pyplot)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    noisy, clean, pm = _cubes(golden, "base")
+    factory = drivers.reference_net_factory(rx.REFERENCE_ROOT, kind, 128)
+    net = factory()
+    n_params = sum(p.numel() for p in net.parameters())
+    if kind == "skip":
+        assert n_params == 3_141_632                                  # SURVEY §2.1
+    with torch.no_grad():
+        assert net(noisy).shape == noisy.shape                        # 36x36 in -> 36x36 out
+    msk = torch.from_numpy(pm.reshape(36, 36).T.reshape(1, 1, 36, 36).astype(np.float32))
+    losses = []
+
+    class Spy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = factory()
+
+        def forward(self, x):
+            out = self.net(x)
+            losses.append(float(torch.nn.functional.mse_loss(noisy * msk, out.detach() * msk)))
+            return out
+
+    hook = drivers.dip_low_rank(Spy, noisy, msk, 36, 36, num_iter=4, lr=0.01)
+    Z = metrics.unfold(noisy)
+    U = hook(Z)
+    assert U.shape == Z.shape and bool(torch.isfinite(U).all())
+    assert len(losses) == 4 and losses[-1] < losses[0]                # Adam on the masked MSE makes progress
+    # the hook's layout shuffles are the reference's (:412, :419): unfold(fold(Z)) == Z
+    assert torch.equal(metrics.unfold(metrics.fold(Z, 36, 36)), Z)
