@@ -73,6 +73,9 @@ constexpr int NTHREADS = 32 * (FIRST_EPI + NEPI);
 #ifndef LRS_DEFER_ARRIVE
 #define LRS_DEFER_ARRIVE 1   // 1: soft chunk j is signalled from the middle of chunk j+1 (hides the TMEM store latency)
 #endif
+#ifndef LRS_SOFT_XORSIGN
+#define LRS_SOFT_XORSIGN 1   // 1: clamp through min.xorsign.abs (one FMNMX.XORSIGN per element)
+#endif
 #ifndef LRS_SOFT_SAT
 #define LRS_SOFT_SAT 0       // 1 / 2: soft threshold through fma.sat on the FMA pipe (see SoftSat; both measured, neither adopted)
 #endif
@@ -175,9 +178,18 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& p1, uin
     p2 = pack_h2(l);
 }
 
-// soft(g, T) = g - clamp(g, -T, T) for a pair (two min/max each, one packed subtract)
+// soft(g, T) = g - clamp(g, -T, T) for a pair.  clamp(g, -T, T) = sign(g) min(|g|, T) is ONE instruction per element
+// (min.xorsign.abs -> FMNMX.XORSIGN: magnitude min(|g|, |T|), sign = sign(g) xor sign(T), T >= 0), then one packed
+// subtract: three instructions per pair, exact (|g| <= T gives g - g = 0; beyond it g -/+ T is the single rounding of
+// sign(g)(|g| - T), soft.m:4).  LRS_SOFT_XORSIGN = 0 keeps the two-min/max form (five instructions per pair).
 __device__ __forceinline__ void soft_pair(float g0, float g1, float T, float& x0, float& x1) {
+#if LRS_SOFT_XORSIGN
+    float t0, t1;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(t0) : "f"(g0), "f"(T));
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(t1) : "f"(g1), "f"(T));
+#else
     const float t0 = fminf(fmaxf(g0, -T), T), t1 = fminf(fmaxf(g1, -T), T);
+#endif
     upk2(sub2(pk2(g0, g1), pk2(t0, t1)), x0, x1);
 }
 // The same through the FMA pipe (the min/max form runs on the half-rate ALU pipe that bounds the epilogue).
