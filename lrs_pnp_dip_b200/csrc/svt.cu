@@ -89,11 +89,57 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     }
 }
 
+// W[i,j] = sum_k V[i,k] w_k V[j,k],  w_k = max(1 - tau/sigma_k, 0),  sigma_k = sqrt(max(lambda_k, 0))  (fp64 sum, fp32 out):
+// the singular-value shrinkage of main_LRS_PnP.py:121-123 expressed on the eigenpairs of the band Gram matrix.  One
+// launch instead of a dozen elementwise / GEMM launches of host code between the eigensolver and the recomposition.
+// V is addressed through its two strides (eigensolvers return column-major eigenvector matrices); only the leading
+// C x C block of the n-eigenpair problem is produced (n > C for a zero-bordered problem, see ops.svt_weights).
+constexpr int WT = 16;
+__global__ void __launch_bounds__(WT * WT) svt_weights_kernel(const double* __restrict__ evals, const double* __restrict__ V,
+                                                              int64_t sr, int64_t sk, int C, int n, double tau,
+                                                              float* __restrict__ W) {
+    __shared__ double Vi[WT][WT + 1], Vj[WT][WT + 1], wk[WT];
+    const int tx = threadIdx.x % WT, ty = threadIdx.x / WT;
+    const int i0 = blockIdx.y * WT, j0 = blockIdx.x * WT;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < n; k0 += WT) {
+        const int k = k0 + tx;
+        Vi[ty][tx] = (i0 + ty < C && k < n) ? V[(int64_t)(i0 + ty) * sr + (int64_t)k * sk] : 0.0;
+        Vj[ty][tx] = (j0 + ty < C && k < n) ? V[(int64_t)(j0 + ty) * sr + (int64_t)k * sk] : 0.0;
+        if (ty == 0) {
+            double w = 0.0;
+            if (k < n) {
+                const double lam = evals[k];
+                const double sigma = lam > 0.0 ? sqrt(lam) : 0.0;
+                w = sigma > tau ? 1.0 - tau / sigma : 0.0;
+                if (!(lam == lam) || lam - lam != 0.0) w = lam;     // NaN / Inf eigenvalues poison W (the caller checks them)
+            }
+            wk[tx] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < WT; ++kk) acc = fma(Vi[ty][kk] * wk[kk], Vj[tx][kk], acc);
+        __syncthreads();
+    }
+    if (i0 + ty < C && j0 + tx < C) W[(int64_t)(i0 + ty) * C + j0 + tx] = (float)acc;
+}
+
 }  // namespace lrs
 
 using namespace lrs;
 
 extern "C" {
+
+int lrs_svt_weights_f64(const double* evals_dev, const double* V_dev, int64_t v_row_stride, int64_t v_col_stride, int C,
+                        int n_eig, double tau, float* W_dev, lrs_stream_t stream) {
+    const char* fn = "lrs_svt_weights_f64";
+    if (C <= 0 || n_eig < C || !evals_dev || !V_dev || !W_dev || v_row_stride == 0 || v_col_stride == 0 || !(tau >= 0.0))
+        return fail_arg(fn, "bad arguments");
+    dim3 grid((unsigned)((C + WT - 1) / WT), (unsigned)((C + WT - 1) / WT));
+    svt_weights_kernel<<<grid, WT * WT, 0, (cudaStream_t)stream>>>(evals_dev, V_dev, v_row_stride, v_col_stride, C, n_eig, tau, W_dev);
+    LRS_CHECK_LAUNCH(fn);
+    return LRS_OK;
+}
 
 int lrs_gram_f64(const float* X_dev, const float* L_dev, float c, int64_t R, int64_t C, double* G_dev,
                  lrs_stream_t stream) {

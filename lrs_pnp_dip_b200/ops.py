@@ -253,19 +253,36 @@ def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "
 
 
 # ------------------------------------------------------------------ SVT
+_EIGH_PAD_FROM, _EIGH_PAD_TO = 96, 136     # band counts in [96, 136) are solved as a zero-bordered order-136 problem
+
+
 def svt_weights(G: torch.Tensor, tau: float) -> torch.Tensor:
     """W = V diag(max(1 - tau/sigma, 0)) Vᵀ from the fp64 Gram matrix (σ² = eig)."""
-    if not bool(torch.isfinite(G).all()):           # eigh synchronises anyway; this names the real cause
-        raise _lib.LrsError("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
-                            "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
-                            "with stride-1 overlap it grows geometrically and overflows fp32 after ~20 outer iterations)")
+    C = G.shape[0]
+    G0 = G
+    if _EIGH_PAD_FROM <= C < _EIGH_PAD_TO:
+        # cuSOLVER's syevd back-transforms the eigenvectors of orders <= ~128 with unblocked gemv/gerc pairs (126 pairs,
+        # 1.3 of the 2.1 ms at C = 128, scripts/eigh_time.py); from order 136 on it takes the blocked path (1.1 ms).  A
+        # zero border adds decoupled zero eigenvalues, whose weight is 0 (sigma = 0 <= tau): W's leading block is unchanged.
+        Gp = torch.zeros((_EIGH_PAD_TO, _EIGH_PAD_TO), dtype=G.dtype, device=G.device)
+        Gp[:C, :C] = G
+        G = Gp
+    diverged = ("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
+                "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
+                "with stride-1 overlap it grows geometrically and overflows fp32 after ~20 outer iterations)")
     try:
         evals, V = torch.linalg.eigh(G)
     except RuntimeError as e:                       # torch.linalg.LinAlgError is a RuntimeError
-        raise _lib.LrsError(f"SVT: eigh of the {G.shape[0]}x{G.shape[0]} band Gram matrix failed: {e}") from e
-    sigma = evals.clamp_min(0).sqrt()
-    w = torch.where(sigma > tau, 1.0 - tau / sigma.clamp_min(1e-300), torch.zeros_like(sigma))
-    return ((V * w[None, :]) @ V.T).to(torch.float32).contiguous()
+        if not bool(torch.isfinite(G0).all()):      # name the real cause
+            raise _lib.LrsError(diverged) from e
+        raise _lib.LrsError(f"SVT: eigh of the {C}x{C} band Gram matrix failed: {e}") from e
+    # eigh has synchronised on its status word: the eigenvalues are ready, reading them back costs one small copy
+    if not bool(torch.isfinite(evals.cpu()).all()):
+        raise _lib.LrsError(diverged)
+    W = torch.empty((C, C), dtype=torch.float32, device=G.device)
+    check(lib().lrs_svt_weights_f64(ptr(evals), ptr(V), V.stride(0), V.stride(1), C, G.shape[0], float(tau), ptr(W),
+                                    stream_ptr()), "lrs_svt_weights_f64")
+    return W
 
 
 def svt_device(X: torch.Tensor, tau: float, lambda_2: Optional[torch.Tensor] = None, c: float = 0.0,

@@ -135,6 +135,17 @@ def _range_pipe(device) -> _RangePipe:
     return _RANGE_PIPES[key]
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """One extra stream per device for the low-rank step that runs beside the explicit sparse step (LRSPnP._step)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=torch.device("cuda", key))
+    return _SIDE_STREAMS[key]
+
+
 class SparseCoder:
     """Everything of the sparse step that depends only on (Y_observed, D, geometry): the per-patch
     validity masks (``blocks_copy == 0``, main_LRS_PnP.py:244,276-280) and the ISTA step constants,
@@ -436,6 +447,14 @@ class LRSPnP:
         self.lambda_1 = torch.zeros_like(Y_observed)     # (:219)
         self.lambda_2 = torch.zeros_like(Y_observed)     # (:220)
         self.iterations = 0
+        # The low-rank step reads (X, λ2) and the sparse step reads (X, λ1): the two are independent until the X / λ
+        # update (SURVEY §1, L2 ‖ L3).  With the explicit engine (a chain of short launches that leaves SMs idle) the
+        # low-rank step — Gram, eigh, recomposition, or the caller's network — runs on a second stream beside it.  The
+        # fused engines keep every SM busy with persistent CTAs (nothing could run beside them): sequential there.
+        coder = getattr(backend, "coder", None)
+        self.overlap_low_rank = (isinstance(backend, CudaBackend) and coder is not None and not coder.fused
+                                 and self.stripe.world == 1)
+        self._side = None
 
     @property
     def rows_owned(self) -> int:
@@ -458,16 +477,30 @@ class LRSPnP:
         prm, st, be = self.prm, self.stripe, self.be
         own = self.rows_owned
         row_off = st.a if st.world > 1 else 0
-        # sparse step + overlap sum on the local rows (:259-303, :332-339)
-        IMout = be.imout(self.X, self.lambda_1)
-        self.comm.halo_reduce(IMout)
-        # low-rank step on Z = X + (1/mu_2) lambda_2 (:315)
         c = 1.0 / prm.mu_2
-        if self.low_rank is None:
-            G = self.comm.allreduce_sum(be.gram(self.X, self.lambda_2, c, own))
-            U = be.svt_apply(self.X, self.lambda_2, c, G, 1.0 / prm.mu_2, own)
+
+        def low_rank_step():
+            # low-rank step on Z = X + (1/mu_2) lambda_2 (:315)
+            if self.low_rank is None:
+                G = self.comm.allreduce_sum(be.gram(self.X, self.lambda_2, c, own))
+                return be.svt_apply(self.X, self.lambda_2, c, G, 1.0 / prm.mu_2, own)
+            return self.low_rank(be.axpy(self.X, self.lambda_2, c, own))
+
+        if self.overlap_low_rank:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = _side_stream(self.X.device)
+            self._side.wait_stream(main)                 # X, λ2 as the previous iteration left them
+            IMout = be.imout(self.X, self.lambda_1)      # enqueued first: the host may block inside a caller's network
+            with torch.cuda.stream(self._side):
+                U = low_rank_step()
+            main.wait_stream(self._side)
+            U.record_stream(main)                        # allocated on the side stream, consumed on the caller's
         else:
-            U = self.low_rank(be.axpy(self.X, self.lambda_2, c, own))
+            # sparse step + overlap sum on the local rows (:259-303, :332-339)
+            IMout = be.imout(self.X, self.lambda_1)
+            self.comm.halo_reduce(IMout)
+            U = low_rank_step()
         # closed-form X, multipliers (:346, :361-362) on the owned rows
         Xn = be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total)
         self.X[:own] = Xn
