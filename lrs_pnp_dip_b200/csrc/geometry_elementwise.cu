@@ -314,27 +314,64 @@ __global__ void step_frob4_kernel(const float* __restrict__ bc, const float* __r
 }
 
 // X / multiplier update, main_LRS_PnP.py:346,361-362 — same fp32 operation order, no FMA contraction.
+// A thread owns one band of ADMM_RPT consecutive unfolded rows: its 6 x ADMM_RPT loads are issued together and the
+// ADMM_RPT chains of dependent adds of lambda1_summation (:343, one add per covering patch, up to bb^2 = 64 at stride 1)
+// run interleaved, so the add latency of one element hides behind the others'.
+constexpr int ADMM_RPT = 4;
 __global__ void admm_update_kernel(Geom g, const float* __restrict__ Y, const float* __restrict__ M,
                                    const float* __restrict__ IM, const float* __restrict__ U, float* __restrict__ lam1,
                                    float* __restrict__ lam2, float* __restrict__ Xo, float gamma, float mu1, float mu2,
                                    int64_t rows, int64_t row_offset) {
-    const int64_t r = blockIdx.x;                                        // one unfolded row per block row
+    const int64_t r0 = (int64_t)blockIdx.x * ADMM_RPT;                   // ADMM_RPT unfolded rows per block row
     const int64_t c = blockIdx.y * (int64_t)blockDim.x + threadIdx.x;    // bands along the threads (coalesced)
-    if (r >= rows || c >= g.C) return;
-    const int64_t idx = r * g.C + c;
-    int W = g.row.count(r + row_offset) * g.col.count(c);
-    float l1 = lam1[idx], l2 = lam2[idx], im = IM[idx], u = U[idx];
-    float l1s = 0.0f;
-    for (int t = 0; t < W; ++t) l1s = __fadd_rn(l1s, l1);  // lambda1_summation (:343), one add per covering patch
-    float num = __fadd_rn(__fmul_rn(gamma, Y[idx]), __fmul_rn(mu1, im));
-    num = __fadd_rn(num, __fmul_rn(mu2, u));
-    num = __fsub_rn(num, l1s);
-    num = __fsub_rn(num, l2);
-    float den = __fadd_rn(__fadd_rn(__fmul_rn(gamma, M[idx]), __fmul_rn(mu1, (float)W)), mu2);
-    float x = __fdiv_rn(num, den);
-    Xo[idx] = x;
-    lam1[idx] = __fadd_rn(l1, __fmul_rn(mu1, __fsub_rn(x, im)));
-    lam2[idx] = __fadd_rn(l2, __fmul_rn(mu2, __fsub_rn(x, u)));
+    if (c >= g.C) return;
+    const int wc = g.col.count(c);
+    float l1[ADMM_RPT], l2[ADMM_RPT], im[ADMM_RPT], u[ADMM_RPT], y[ADMM_RPT], m[ADMM_RPT], l1s[ADMM_RPT];
+    int W[ADMM_RPT], wmax = 0;
+#pragma unroll
+    for (int k = 0; k < ADMM_RPT; ++k) {
+        const bool ok = r0 + k < rows;
+        const int64_t idx = (ok ? r0 + k : r0) * g.C + c;
+        W[k] = ok ? g.row.count(r0 + k + row_offset) * wc : 0;
+        wmax = W[k] > wmax ? W[k] : wmax;
+        l1[k] = lam1[idx];
+        l2[k] = lam2[idx];
+        im[k] = __ldg(IM + idx);
+        u[k] = __ldg(U + idx);
+        y[k] = __ldg(Y + idx);
+        m[k] = __ldg(M + idx);
+        l1s[k] = 0.0f;
+    }
+    bool uniform = true;
+#pragma unroll
+    for (int k = 0; k < ADMM_RPT; ++k) uniform = uniform && W[k] == wmax;
+    if (uniform) {               // interior rows: every element is covered equally often — no per-add predicate
+#pragma unroll 8
+        for (int t = 0; t < wmax; ++t) {
+#pragma unroll
+            for (int k = 0; k < ADMM_RPT; ++k) l1s[k] = __fadd_rn(l1s[k], l1[k]);  // lambda1_summation (:343)
+        }
+    } else {
+        for (int t = 0; t < wmax; ++t) {
+#pragma unroll
+            for (int k = 0; k < ADMM_RPT; ++k)
+                if (t < W[k]) l1s[k] = __fadd_rn(l1s[k], l1[k]);  // one add per covering patch
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ADMM_RPT; ++k) {
+        if (r0 + k >= rows) break;
+        const int64_t idx = (r0 + k) * g.C + c;
+        float num = __fadd_rn(__fmul_rn(gamma, y[k]), __fmul_rn(mu1, im[k]));
+        num = __fadd_rn(num, __fmul_rn(mu2, u[k]));
+        num = __fsub_rn(num, l1s[k]);
+        num = __fsub_rn(num, l2[k]);
+        const float den = __fadd_rn(__fadd_rn(__fmul_rn(gamma, m[k]), __fmul_rn(mu1, (float)W[k])), mu2);
+        const float x = __fdiv_rn(num, den);
+        Xo[idx] = x;
+        lam1[idx] = __fadd_rn(l1[k], __fmul_rn(mu1, __fsub_rn(x, im[k])));
+        lam2[idx] = __fadd_rn(l2[k], __fmul_rn(mu2, __fsub_rn(x, u[k])));
+    }
 }
 
 static inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -500,7 +537,7 @@ int lrs_admm_update_f32(const float* Y_dev, const float* MtM_dev, const float* i
     if (!Y_dev || !MtM_dev || !imout_dev || !U_dev || !lam1_dev || !lam2_dev || !X_out_dev)
         return fail_arg("lrs_admm_update_f32", "null pointer");
     const int threads = C >= 256 ? 256 : (int)((C + 31) / 32 * 32);
-    dim3 grid((unsigned)rows, blocks_for(C, threads));
+    dim3 grid((unsigned)((rows + ADMM_RPT - 1) / ADMM_RPT), blocks_for(C, threads));
     if (rows > 2147483647LL || grid.y > 65535) return fail_arg("lrs_admm_update_f32", "matrix too large");
     admm_update_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(g, Y_dev, MtM_dev, imout_dev, U_dev, lam1_dev, lam2_dev,
                                                                   X_out_dev, gamma, mu_1, mu_2, rows, row_offset);
