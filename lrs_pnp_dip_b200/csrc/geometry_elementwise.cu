@@ -257,11 +257,14 @@ __global__ void __launch_bounds__(TR * TY, 1536 / (TR * TY)) col2im_kernel(Geom 
     }
 }
 
+constexpr int WEIGHT_ROWS = 32;     // unfolded rows per block (a block per row is launch-overhead bound: 21 % of the HBM peak)
 __global__ void weight_kernel(Geom g, float* __restrict__ w) {
-    const int64_t r = blockIdx.x;                                        // one unfolded row per block row
+    const int64_t r0 = (int64_t)blockIdx.x * WEIGHT_ROWS;
     const int64_t c = blockIdx.y * (int64_t)blockDim.x + threadIdx.x;    // bands along the threads
     if (c >= g.C) return;
-    w[r * g.C + c] = (float)(g.row.count(r) * g.col.count(c));
+    const int wc = g.col.count(c);
+    const int64_t r1 = r0 + WEIGHT_ROWS < g.R ? r0 + WEIGHT_ROWS : g.R;
+    for (int64_t r = r0; r < r1; ++r) w[r * g.C + c] = (float)(g.row.count(r) * wc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -476,7 +479,7 @@ int lrs_coverage_weight_f32(int64_t R, int64_t C, int bb, int s, float* weight_d
     if (!make_geom(R, C, bb, s, g)) return fail_arg("lrs_coverage_weight_f32", "need 0 < bb <= min(R,C) and s > 0");
     if (!weight_dev) return fail_arg("lrs_coverage_weight_f32", "null pointer");
     const int threads = C >= 256 ? 256 : (int)((C + 31) / 32 * 32);
-    dim3 grid((unsigned)R, blocks_for(C, threads));
+    dim3 grid(blocks_for(R, WEIGHT_ROWS), blocks_for(C, threads));
     if (R > 2147483647LL || grid.y > 65535) return fail_arg("lrs_coverage_weight_f32", "matrix too large");
     weight_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(g, weight_dev);
     LRS_CHECK_LAUNCH("lrs_coverage_weight_f32");
