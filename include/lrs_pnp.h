@@ -165,11 +165,18 @@ int lrs_admm_update_f32(const float* Y_dev, const float* MtM_dev, const float* i
 /* G[C,C] (fp64, device, accumulated INTO — caller zeroes) += Z^T Z with Z = X + c*L (L may be NULL). */
 int lrs_gram_f64(const float* X_dev, const float* L_dev, float c, int64_t R, int64_t C, double* G_dev,
                  lrs_stream_t stream);
+/* Symmetric eigen-decomposition of the band Gram matrix (fp64, symmetric positive semi-definite, 1 <= C <= 256) in ONE
+ * launch: one-sided Jacobi over a thread-block cluster (csrc/jacobi_eig.cu) — replaces the eigh / SVD of
+ * main_LRS_PnP.py:119 without a host synchronisation.  Outputs: lam_dev[C] eigenvalues (unsorted), Bt_dev[C*C] with row k
+ * = lambda_k * v_k (the eigenvector scaled by its eigenvalue; "B form"), status_dev[3] = {sweeps run, 1 if not converged,
+ * 1 if an eigenvalue is not finite}. */
+int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_dev, double* Bt_dev, int* status_dev, lrs_stream_t stream);
 /* W[C,C] (f32) = V diag(max(1 - tau/sigma_k, 0)) V^T on the leading C x C block, sigma_k = sqrt(max(evals[k], 0)):
  * the shrinkage of main_LRS_PnP.py:121-123 on the n_eig >= C eigenpairs of the (possibly zero-bordered) Gram matrix.
- * V[i,k] is read at V_dev[i*v_row_stride + k*v_col_stride] (eigenvectors in columns, either storage order). */
+ * V[i,k] is read at V_dev[i*v_row_stride + k*v_col_stride] (eigenvectors in columns, either storage order).
+ * b_form != 0: column k holds lambda_k * v_k as lrs_sym_eig_jacobi_f64 returns it (v_row_stride = 1, v_col_stride = C). */
 int lrs_svt_weights_f64(const double* evals_dev, const double* V_dev, int64_t v_row_stride, int64_t v_col_stride, int C,
-                        int n_eig, double tau, float* W_dev, lrs_stream_t stream);
+                        int n_eig, double tau, int b_form, float* W_dev, lrs_stream_t stream);
 /* U[R,C] = (X + c*L) * W, W [C,C] f32 = V diag(max(1 - tau/sigma, 0)) V^T from the caller's eigh. */
 int lrs_svt_apply_f32(const float* X_dev, const float* L_dev, float c, const float* W_dev, int64_t R, int64_t C,
                       float* U_dev, lrs_stream_t stream);

@@ -49,7 +49,8 @@ SIGNATURES = {
                                          _i64, _p, _int, _p]),
     "lrs_admm_update_f32": (_int, [_p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i64, _i64, _i64, _i64, _int, _int, _p]),
     "lrs_gram_f64": (_int, [_p, _p, _f, _i64, _i64, _p, _p]),
-    "lrs_svt_weights_f64": (_int, [_p, _p, _i64, _i64, _int, _int, C.c_double, _p, _p]),
+    "lrs_sym_eig_jacobi_f64": (_int, [_p, _int, _p, _p, _p, _p]),
+    "lrs_svt_weights_f64": (_int, [_p, _p, _i64, _i64, _int, _int, C.c_double, _int, _p, _p]),
     "lrs_svt_apply_f32": (_int, [_p, _p, _f, _p, _i64, _i64, _p, _p]),
 }
 

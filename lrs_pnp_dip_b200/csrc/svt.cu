@@ -94,13 +94,26 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
 // launch instead of a dozen elementwise / GEMM launches of host code between the eigensolver and the recomposition.
 // V is addressed through its two strides (eigensolvers return column-major eigenvector matrices); only the leading
 // C x C block of the n-eigenpair problem is produced (n > C for a zero-bordered problem, see ops.svt_weights).
+// BFORM: column k of V holds b_k = lambda_k v_k (the one-sided Jacobi solver, jacobi_eig.cu), so w_k is divided by
+// lambda_k^2; directions that are numerically zero (lambda_k <= 1e-12 lambda_max: b_k is rounding noise) get weight 0.
 constexpr int WT = 16;
+template <bool BFORM>
 __global__ void __launch_bounds__(WT * WT) svt_weights_kernel(const double* __restrict__ evals, const double* __restrict__ V,
                                                               int64_t sr, int64_t sk, int C, int n, double tau,
                                                               float* __restrict__ W) {
-    __shared__ double Vi[WT][WT + 1], Vj[WT][WT + 1], wk[WT];
+    __shared__ double Vi[WT][WT + 1], Vj[WT][WT + 1], wk[WT], red[WT * WT / 32];
     const int tx = threadIdx.x % WT, ty = threadIdx.x / WT;
     const int i0 = blockIdx.y * WT, j0 = blockIdx.x * WT;
+    double cut = 0.0;
+    if (BFORM) {
+        double mx = 0.0;
+        for (int k = threadIdx.x; k < n; k += WT * WT) mx = fmax(mx, evals[k]);      // fmax drops NaN: handled per k below
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        for (int q = 0; q < WT * WT / 32; ++q) cut = fmax(cut, red[q]);
+        cut *= 1e-12;
+    }
     double acc = 0.0;
     for (int k0 = 0; k0 < n; k0 += WT) {
         const int k = k0 + tx;
@@ -112,7 +125,8 @@ __global__ void __launch_bounds__(WT * WT) svt_weights_kernel(const double* __re
                 const double lam = evals[k];
                 const double sigma = lam > 0.0 ? sqrt(lam) : 0.0;
                 w = sigma > tau ? 1.0 - tau / sigma : 0.0;
-                if (!(lam == lam) || lam - lam != 0.0) w = lam;     // NaN / Inf eigenvalues poison W (the caller checks them)
+                if (BFORM) w = lam > cut ? w / (lam * lam) : 0.0;
+                if (!(lam - lam == 0.0)) w = lam - lam;             // NaN / Inf eigenvalues poison W (the caller checks them)
             }
             wk[tx] = w;
         }
@@ -131,12 +145,15 @@ using namespace lrs;
 extern "C" {
 
 int lrs_svt_weights_f64(const double* evals_dev, const double* V_dev, int64_t v_row_stride, int64_t v_col_stride, int C,
-                        int n_eig, double tau, float* W_dev, lrs_stream_t stream) {
+                        int n_eig, double tau, int b_form, float* W_dev, lrs_stream_t stream) {
     const char* fn = "lrs_svt_weights_f64";
     if (C <= 0 || n_eig < C || !evals_dev || !V_dev || !W_dev || v_row_stride == 0 || v_col_stride == 0 || !(tau >= 0.0))
         return fail_arg(fn, "bad arguments");
     dim3 grid((unsigned)((C + WT - 1) / WT), (unsigned)((C + WT - 1) / WT));
-    svt_weights_kernel<<<grid, WT * WT, 0, (cudaStream_t)stream>>>(evals_dev, V_dev, v_row_stride, v_col_stride, C, n_eig, tau, W_dev);
+    if (b_form)
+        svt_weights_kernel<true><<<grid, WT * WT, 0, (cudaStream_t)stream>>>(evals_dev, V_dev, v_row_stride, v_col_stride, C, n_eig, tau, W_dev);
+    else
+        svt_weights_kernel<false><<<grid, WT * WT, 0, (cudaStream_t)stream>>>(evals_dev, V_dev, v_row_stride, v_col_stride, C, n_eig, tau, W_dev);
     LRS_CHECK_LAUNCH(fn);
     return LRS_OK;
 }

@@ -253,12 +253,61 @@ def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "
 
 
 # ------------------------------------------------------------------ SVT
-_EIGH_PAD_FROM, _EIGH_PAD_TO = 96, 136     # band counts in [96, 136) are solved as a zero-bordered order-136 problem
+_EIGH_PAD_FROM, _EIGH_PAD_TO = 96, 136     # library path: band counts in [96, 136) are solved as a zero-bordered order-136 problem
+JACOBI_MAX_C = 256                         # lrs_sym_eig_jacobi_f64: one cluster, columns in distributed shared memory
+JACOBI_AUTO_C = 128                        # solver='auto' takes the Jacobi kernel up to this order (scripts/jacobi_time.py:
+#                                            0.20 / 0.37 / 0.91 ms against 0.35 / 0.99 / 1.14-1.2 ms of syevd at C = 31 / 64 / 128, and no host
+#                                            synchronisation; at C = 191 / 224 / 256 the library is as fast or faster: 1.74 / 2.4 / 3.2 vs 1.7 / 2.1 / 2.4 ms)
+
+_DIVERGED = ("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
+             "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
+             "with stride-1 overlap it grows geometrically and overflows fp32 after ~20 outer iterations)")
 
 
-def svt_weights(G: torch.Tensor, tau: float) -> torch.Tensor:
-    """W = V diag(max(1 - tau/sigma, 0)) Vᵀ from the fp64 Gram matrix (σ² = eig)."""
+def raise_for_eig_status(status) -> None:
+    """``status`` = the three host ints of lrs_sym_eig_jacobi_f64: sweeps, not-converged flag, non-finite flag."""
+    sweeps, unconverged, nonfinite = (int(v) for v in status)
+    if nonfinite:
+        raise _lib.LrsError(_DIVERGED)
+    if unconverged:
+        raise _lib.LrsError(f"SVT: the Jacobi eigensolver still rotated after {sweeps} sweeps")
+
+
+def sym_eig_jacobi(G: torch.Tensor):
+    """(lam [C], Bt [C, C], status [3] int32) of lrs_sym_eig_jacobi_f64 for a symmetric PSD fp64 matrix on the device:
+    row k of Bt is lam[k] * v_k.  No host synchronisation."""
     C = G.shape[0]
+    if G.dtype != torch.float64 or G.shape != (C, C) or not 1 <= C <= JACOBI_MAX_C:
+        raise ValueError("sym_eig_jacobi needs a square fp64 matrix of order 1..256")
+    G = G.contiguous()
+    lam = torch.empty(C, dtype=torch.float64, device=G.device)
+    Bt = torch.empty((C, C), dtype=torch.float64, device=G.device)
+    status = torch.empty(3, dtype=torch.int32, device=G.device)
+    check(lib().lrs_sym_eig_jacobi_f64(ptr(G), C, ptr(lam), ptr(Bt), ptr(status), stream_ptr()), "lrs_sym_eig_jacobi_f64")
+    return lam, Bt, status
+
+
+def svt_weights(G: torch.Tensor, tau: float, solver: str = "auto", status_sink=None) -> torch.Tensor:
+    """W = V diag(max(1 - tau/sigma, 0)) Vᵀ from the fp64 Gram matrix (σ² = eig).
+
+    ``solver``: 'jacobi' = the cluster Jacobi kernel (C <= 256, one launch, no host synchronisation), 'library' =
+    torch.linalg.eigh (cuSOLVER syevd, synchronises on its status word), 'auto' = jacobi up to JACOBI_AUTO_C bands.
+    ``status_sink``: with the Jacobi solver the device status words are handed to this callable instead of being read
+    back here (the ADMM driver looks at them later, without stalling the step); None = check now (one small copy)."""
+    C = G.shape[0]
+    if solver == "auto":
+        solver = "jacobi" if C <= JACOBI_AUTO_C else "library"
+    W = torch.empty((C, C), dtype=torch.float32, device=G.device)
+    if solver == "jacobi":
+        lam, Bt, status = sym_eig_jacobi(G)
+        check(lib().lrs_svt_weights_f64(ptr(lam), ptr(Bt), 1, C, C, C, float(tau), 1, ptr(W), stream_ptr()), "lrs_svt_weights_f64")
+        if status_sink is None:
+            raise_for_eig_status(status.cpu())
+        else:
+            status_sink(status)
+        return W
+    if solver != "library":
+        raise ValueError(solver)
     G0 = G
     if _EIGH_PAD_FROM <= C < _EIGH_PAD_TO:
         # cuSOLVER's syevd back-transforms the eigenvectors of orders <= ~128 with unblocked gemv/gerc pairs (126 pairs,
@@ -267,20 +316,16 @@ def svt_weights(G: torch.Tensor, tau: float) -> torch.Tensor:
         Gp = torch.zeros((_EIGH_PAD_TO, _EIGH_PAD_TO), dtype=G.dtype, device=G.device)
         Gp[:C, :C] = G
         G = Gp
-    diverged = ("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
-                "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
-                "with stride-1 overlap it grows geometrically and overflows fp32 after ~20 outer iterations)")
     try:
         evals, V = torch.linalg.eigh(G)
     except RuntimeError as e:                       # torch.linalg.LinAlgError is a RuntimeError
         if not bool(torch.isfinite(G0).all()):      # name the real cause
-            raise _lib.LrsError(diverged) from e
+            raise _lib.LrsError(_DIVERGED) from e
         raise _lib.LrsError(f"SVT: eigh of the {C}x{C} band Gram matrix failed: {e}") from e
     # eigh has synchronised on its status word: the eigenvalues are ready, reading them back costs one small copy
     if not bool(torch.isfinite(evals.cpu()).all()):
-        raise _lib.LrsError(diverged)
-    W = torch.empty((C, C), dtype=torch.float32, device=G.device)
-    check(lib().lrs_svt_weights_f64(ptr(evals), ptr(V), V.stride(0), V.stride(1), C, G.shape[0], float(tau), ptr(W),
+        raise _lib.LrsError(_DIVERGED)
+    check(lib().lrs_svt_weights_f64(ptr(evals), ptr(V), V.stride(0), V.stride(1), C, G.shape[0], float(tau), 0, ptr(W),
                                     stream_ptr()), "lrs_svt_weights_f64")
     return W
 

@@ -392,6 +392,7 @@ class CudaBackend:
         self.prm = prm
         self.Y, self.MtM = Y_local, MtM_local
         self.coder = SparseCoder(Y_local, D, prm, engine, defer_validation=True)
+        self._pending: list = []
 
     def imout(self, X, lambda_1):
         return self.coder.imout(X, lambda_1)
@@ -402,8 +403,27 @@ class CudaBackend:
         check(lib().lrs_gram_f64(ptr(X), ptr(lambda_2), float(c), rows, C, ptr(G), stream_ptr()), "lrs_gram_f64")
         return G
 
+    def _defer_status(self, status: torch.Tensor) -> None:
+        """Status words of the Jacobi eigensolver travel to pinned host memory behind the kernels that produced them;
+        check_status() looks at them later (LRSPnP: at the next step and in validate()), so no step waits on the host."""
+        host = torch.empty(3, dtype=torch.int32).pin_memory()
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((host, ev))
+
+    def check_status(self, wait: bool = False) -> None:
+        while self._pending:
+            host, ev = self._pending[0]
+            if wait:
+                ev.synchronize()
+            elif not ev.query():
+                return
+            self._pending.pop(0)
+            ops.raise_for_eig_status(host)
+
     def svt_apply(self, X, lambda_2, c, G, tau, rows):
-        W = ops.svt_weights(G, tau)
+        W = ops.svt_weights(G, tau, status_sink=self._defer_status)
         U = torch.empty((rows, X.shape[1]), dtype=torch.float32, device=X.device)
         check(lib().lrs_svt_apply_f32(ptr(X), ptr(lambda_2), float(c), ptr(W), rows, X.shape[1], ptr(U), stream_ptr()),
               "lrs_svt_apply_f32")
@@ -475,6 +495,8 @@ class LRSPnP:
 
     def _step(self) -> None:
         prm, st, be = self.prm, self.stripe, self.be
+        if hasattr(be, "check_status"):
+            be.check_status(wait=False)                  # deferred eigensolver verdicts of earlier steps (no stall)
         own = self.rows_owned
         row_off = st.a if st.world > 1 else 0
         c = 1.0 / prm.mu_2
@@ -491,9 +513,17 @@ class LRSPnP:
             if self._side is None:
                 self._side = _side_stream(self.X.device)
             self._side.wait_stream(main)                 # X, λ2 as the previous iteration left them
-            IMout = be.imout(self.X, self.lambda_1)      # enqueued first: the host may block inside a caller's network
-            with torch.cuda.stream(self._side):
-                U = low_rank_step()
+            # The SVT through the Jacobi kernel never blocks the host: it is enqueued first and runs from the start of the
+            # sparse step.  A caller's network or the library eigensolver may block (early stop, status word): then the
+            # sparse step is enqueued first.
+            lr_async = self.low_rank is None and self.X.shape[1] <= ops.JACOBI_AUTO_C
+            if lr_async:
+                with torch.cuda.stream(self._side):
+                    U = low_rank_step()
+            IMout = be.imout(self.X, self.lambda_1)
+            if not lr_async:
+                with torch.cuda.stream(self._side):
+                    U = low_rank_step()
             main.wait_stream(self._side)
             U.record_stream(main)                        # allocated on the side stream, consumed on the caller's
         else:
@@ -512,6 +542,8 @@ class LRSPnP:
         coder = getattr(self.be, "coder", None)
         if coder is not None:
             coder.validate()
+        if hasattr(self.be, "check_status"):
+            self.be.check_status(wait=True)
 
     def run(self, iteration_num: int) -> "LRSPnP":
         for _ in range(iteration_num):
