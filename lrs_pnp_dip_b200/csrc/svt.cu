@@ -14,11 +14,14 @@ constexpr int GT = 64;       // output tile (bands x bands)
 constexpr int GROWS = 16;    // rows staged per step
 
 // grid.x = upper-triangular tile pairs, grid.y = row chunks.  256 threads, 4x4 fp64 accumulators each.
+// The tiles are staged as fp64 (one conversion per loaded element instead of one per use: with fp32 tiles the F2F
+// conversions, not the DFMA pipe, bound the kernel) and a thread's 4 + 4 operands are 16 columns apart, so the 16 lanes
+// that differ in tx read 128 contiguous bytes (one wavefront) and the lanes that share ty read one broadcast word.
 __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, const float* __restrict__ L, float c,
                                                    int64_t R, int64_t C, int ntile, int64_t rows_per_block,
                                                    double* __restrict__ G) {
-    __shared__ float Zi[GROWS][GT + 4];
-    __shared__ float Zj[GROWS][GT + 4];
+    __shared__ double Zi[GROWS][GT];
+    __shared__ double Zj[GROWS][GT];
     // decode (ti <= tj) from the linear pair index
     int pair = blockIdx.x, ti = 0;
     while (pair >= ntile - ti) {
@@ -35,35 +38,48 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += GROWS) {
+    // software pipeline: the global loads of stage s+1 are in flight while stage s is multiplied (a block's stages would
+    // otherwise each expose one DRAM latency: load -> barrier -> 16 x 16 DFMA -> barrier)
+    constexpr int EPT = GROWS * GT / 256;                      // staged elements per thread and operand
+    float vi[EPT], vj[EPT];
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
-        for (int e = tid; e < GROWS * GT; e += 256) {
-            int rr = e / GT, cc = e % GT;
-            int64_t r = r0 + rr;
-            float vi = 0.f, vj = 0.f;
+        for (int q = 0; q < EPT; ++q) {
+            const int e = tid + 256 * q, rr = e / GT, cc = e % GT;
+            const int64_t r = r0 + rr;
+            vi[q] = 0.f;
+            vj[q] = 0.f;
             if (r < r_end) {
                 if (ci0 + cc < C) {
                     int64_t o = r * C + ci0 + cc;
-                    vi = __ldg(X + o);
-                    if (L) vi = __fadd_rn(vi, __fmul_rn(c, __ldg(L + o)));
+                    vi[q] = __ldg(X + o);
+                    if (L) vi[q] = __fadd_rn(vi[q], __fmul_rn(c, __ldg(L + o)));
                 }
                 if (cj0 + cc < C) {
                     int64_t o = r * C + cj0 + cc;
-                    vj = __ldg(X + o);
-                    if (L) vj = __fadd_rn(vj, __fmul_rn(c, __ldg(L + o)));
+                    vj[q] = __ldg(X + o);
+                    if (L) vj[q] = __fadd_rn(vj[q], __fmul_rn(c, __ldg(L + o)));
                 }
             }
-            Zi[rr][cc] = vi;
-            Zj[rr][cc] = vj;
+        }
+    };
+    fetch(r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += GROWS) {
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            const int e = tid + 256 * q, rr = e / GT, cc = e % GT;
+            Zi[rr][cc] = (double)vi[q];
+            Zj[rr][cc] = (double)vj[q];
         }
         __syncthreads();
+        if (r0 + GROWS < r_end) fetch(r0 + GROWS);
 #pragma unroll
         for (int rr = 0; rr < GROWS; ++rr) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = (double)Zi[rr][ty * 4 + i];
+            for (int i = 0; i < 4; ++i) a[i] = Zi[rr][ty + 16 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = (double)Zj[rr][tx * 4 + j];
+            for (int j = 0; j < 4; ++j) b[j] = Zj[rr][tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -73,11 +89,11 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ X, 
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int64_t gi = ci0 + ty * 4 + i;
+        int64_t gi = ci0 + ty + 16 * i;
         if (gi >= C) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int64_t gj = cj0 + tx * 4 + j;
+            int64_t gj = cj0 + tx + 16 * j;
             if (gj >= C) continue;
             if (ti == tj) {
                 atomicAdd(G + gi * C + gj, acc[i][j]);  // diagonal tile computes both triangles itself
@@ -166,8 +182,10 @@ int lrs_gram_f64(const float* X_dev, const float* L_dev, float c, int64_t R, int
     if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
     int ntile = (int)((C + GT - 1) / GT);
     int npairs = ntile * (ntile + 1) / 2;
-    // enough row chunks to give every SM a few blocks, but at least 256 rows each
-    int64_t want_chunks = ((int64_t)sms * 4 + npairs - 1) / npairs;
+    // row chunks: two whole waves of the 2 blocks an SM holds (126 registers x 256 threads) — 594 blocks on 296 slots ran
+    // as three waves for two waves' worth of work — and at least 256 rows each
+    int64_t want_chunks = ((int64_t)sms * 2 * 2) / npairs;
+    if (want_chunks < 1) want_chunks = 1;
     int64_t rows_per_block = (R + want_chunks - 1) / want_chunks;
     if (rows_per_block < 256) rows_per_block = 256;
     rows_per_block = (rows_per_block + GROWS - 1) / GROWS * GROWS;
