@@ -387,16 +387,12 @@ def run_ours(args, rank, world, local_rank):
 
         def e2e_step():
             nonlocal h2d, d2h
-            dY, dM = hY.to(dev, non_blocking=True), hM.to(dev, non_blocking=True)
-            s2 = lrs.LRSPnP(dY, dM, Dd, prm, engine=args.engine, stripe=st if world > 1 else None, device=dev)
-            s2.X.copy_(hX, non_blocking=True)
-            s2.lambda_1.copy_(hL1, non_blocking=True)
-            s2.lambda_2.copy_(hL2, non_blocking=True)
+            # host-facing call: pinned host buffers in (observation, mask, full ADMM state), one outer iteration, state out
+            s2 = lrs.LRSPnP.from_host(hY, hM, Dd, prm, state=(hX, hL1, hL2), engine=args.engine,
+                                      stripe=st if world > 1 else None, device=dev)
             s2.step()
             e2e_solvers.append(s2.be.coder)
-            oX.copy_(s2.X, non_blocking=True)
-            oL1.copy_(s2.lambda_1, non_blocking=True)
-            oL2.copy_(s2.lambda_2, non_blocking=True)
+            s2.to_host(oX, oL1, oL2)
             h2d = 5 * hY.numel() * 4
             d2h = 3 * hY.numel() * 4
 
@@ -594,10 +590,10 @@ def run_cfg1_ours(args):
     oX = torch.empty_like(hY).pin_memory()
 
     def e2e_step():
-        s2 = lrs.LRSPnP(hY.to(dev, non_blocking=True), hM.to(dev, non_blocking=True), Dd, prm, engine=args.engine, device=dev)
+        s2 = lrs.LRSPnP.from_host(hY, hM, Dd, prm, engine=args.engine, device=dev)
         s2.overlap_low_rank = sol.overlap_low_rank
         s2.step()
-        oX.copy_(s2.X, non_blocking=True)
+        s2.to_host(oX)
 
     e2e_step()
     torch.cuda.synchronize()

@@ -475,6 +475,46 @@ class LRSPnP:
         self.overlap_low_rank = (isinstance(backend, CudaBackend) and coder is not None and not coder.fused
                                  and self.stripe.world == 1)
         self._side = None
+        self._late_inputs = None                         # from_host(): MtM / λ2 uploads still in flight on the side stream
+
+    @classmethod
+    def from_host(cls, Y_observed, MtM, D, prm: Params, state=None, device=None, **kw) -> "LRSPnP":
+        """Solver for HOST inputs (pinned CPU tensors; ``state`` = optional ``(X, lambda_1, lambda_2)`` to resume from).
+        What the sparse step needs (Y_observed, X, λ1) is uploaded on the caller's stream; MtM and λ2, which only the
+        low-rank step and the X / λ update read, travel on a second stream while the sparse step already runs
+        (:meth:`_step` waits for them where they are first used)."""
+        _lib.require_cuda()
+        device = torch.device(device if device is not None else "cuda")
+        as_f32 = lambda t: torch.as_tensor(t, dtype=torch.float32)          # noqa: E731
+        hY, hM = as_f32(Y_observed), as_f32(MtM)
+        with torch.cuda.device(device):
+            main = torch.cuda.current_stream()
+            side = _side_stream(device)
+            dY = hY.to(device, non_blocking=True)
+            dM = torch.empty(hM.shape, dtype=torch.float32, device=device)
+            side.wait_stream(main)                       # the blocks just handed out may have pending work of a former owner
+            with torch.cuda.stream(side):
+                dM.copy_(hM, non_blocking=True)
+            self = cls(dY, dM, D, prm, device=device, **kw)
+            if state is not None:
+                hX, hL1, hL2 = (as_f32(t) for t in state)
+                self.X.copy_(hX, non_blocking=True)
+                self.lambda_1.copy_(hL1, non_blocking=True)
+                side.wait_stream(main)                   # the constructor zero-filled λ2 on the caller's stream
+                with torch.cuda.stream(side):
+                    self.lambda_2.copy_(hL2, non_blocking=True)
+            self._late_inputs = torch.cuda.Event()
+            self._late_inputs.record(side)
+        return self
+
+    def to_host(self, X_out, lambda_1_out=None, lambda_2_out=None) -> None:
+        """Asynchronous copies of the state into (pinned) host tensors on the current stream."""
+        with _on(self.X):
+            X_out.copy_(self.X, non_blocking=True)
+            if lambda_1_out is not None:
+                lambda_1_out.copy_(self.lambda_1, non_blocking=True)
+            if lambda_2_out is not None:
+                lambda_2_out.copy_(self.lambda_2, non_blocking=True)
 
     @property
     def rows_owned(self) -> int:
@@ -519,7 +559,7 @@ class LRSPnP:
             lr_async = self.low_rank is None and self.X.shape[1] <= ops.JACOBI_AUTO_C
             if lr_async:
                 with torch.cuda.stream(self._side):
-                    U = low_rank_step()
+                    U = low_rank_step()                  # (the side stream also carried the late uploads: in order)
             IMout = be.imout(self.X, self.lambda_1)
             if not lr_async:
                 with torch.cuda.stream(self._side):
@@ -530,8 +570,11 @@ class LRSPnP:
             # sparse step + overlap sum on the local rows (:259-303, :332-339)
             IMout = be.imout(self.X, self.lambda_1)
             self.comm.halo_reduce(IMout)
+            if self._late_inputs is not None:
+                torch.cuda.current_stream().wait_event(self._late_inputs)     # MtM, λ2 of from_host()
             U = low_rank_step()
         # closed-form X, multipliers (:346, :361-362) on the owned rows
+        self._late_inputs = None                         # every later use is ordered behind this step on the caller's stream
         Xn = be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total)
         self.X[:own] = Xn
         self.comm.halo_refresh(self.X, self.lambda_1)
