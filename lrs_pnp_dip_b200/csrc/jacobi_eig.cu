@@ -33,7 +33,6 @@ constexpr int JC = 8;              // CTAs per cluster (portable maximum)
 constexpr int JNB = 2 * JC;        // column blocks
 constexpr int JMAXW = 16;          // columns per block  -> C <= 256
 constexpr int JT = 32 * JMAXW;     // one warp per column pair of a sub-round
-constexpr int JROWS = 8;           // rows per lane (C <= 256)
 
 // Orthogonalise columns p and q (n rows each, in shared memory) — one warp.  Returns the squared cosine of the angle it
 // removed (0 if the pair was left alone).
@@ -42,6 +41,7 @@ constexpr int JROWS = 8;           // rows per lane (C <= 256)
 //            decay to rounding noise, which would otherwise be rotated against itself sweep after sweep
 // The rotation angle costs one rsqrt, one reciprocal and one more rsqrt in fp64 (no division, no sqrt): the scalar chain
 // of a pair is what bounds a sub-round, not the column arithmetic.
+template <int JROWS>   // rows per lane: ceil(C / 32) rounded up to even
 __device__ __forceinline__ float rotate_pair(double* __restrict__ p, double* __restrict__ q, int n, int lane, double tol2,
                                             double floor2) {
     double bp[JROWS], bq[JROWS];
@@ -139,6 +139,7 @@ __device__ __forceinline__ void jbar_wait(uint64_t* bar, uint32_t parity) {
 //   4. wait for the incoming slots (own mbarrier), arm the cluster barrier, switch phase.
 // The stopping rule needs no verification sweep: Jacobi converges quadratically, so a sweep whose largest rotated cosine
 // was below 1e-6 leaves cosines of order 1e-12.
+template <int JROWS>
 __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
     jacobi_eig_kernel(const double* __restrict__ G, int n, int w, double tol2, double stop2, int max_sweeps,
                       double* __restrict__ lam, double* __restrict__ Bt, int* __restrict__ status) {
@@ -187,10 +188,8 @@ __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
     __syncthreads();
     cl.sync();                                             // barriers initialised, every CTA resident before remote traffic
 
-    auto rotate = [&](double* p, double* q) {
-        const float c2 = rotate_pair(p, q, n, lane, tol2, floor2);
-        if (c2 > 0.f && lane == 0) atomicMax(&my_max, __float_as_uint(c2));   // positive floats order like their bits
-    };
+    float wmax = 0.f;                                      // this warp's largest rotated cos^2 of the sweep (uniform in the warp)
+    auto rotate = [&](double* p, double* q) { wmax = fmaxf(wmax, rotate_pair<JROWS>(p, q, n, lane, tol2, floor2)); };
 
     int ph = 0, sweep = 0;
     unsigned uses[2] = {0, 0};
@@ -233,6 +232,11 @@ __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
             }
             // tournament move: top[0] stays, top[1] <- bot[0], top[i] <- top[i-1], bot[i] <- bot[i+1], bot[JC-1] <- top[JC-1]
             const int nph = ph ^ 1;
+            if (round == JNB - 2) {                                // end of the sweep: gather the warps' maxima (off the sub-round path)
+                if (lane == 0 && wmax > 0.f) atomicMax(&my_max, __float_as_uint(wmax));   // positive floats order like their bits
+                wmax = 0.f;
+                __syncthreads();
+            }
             if (armed) cl.barrier_wait();                          // step 2: last round's blocks have landed everywhere
             if (tid == 0) {
                 int top_to, top_slot, bot_to, bot_slot;
@@ -310,15 +314,22 @@ extern "C" int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_de
     if (w > JMAXW) return fail_arg(fn, "need 1 <= C <= 256");
     const size_t smem = (size_t)4 * ((size_t)w * C + 2) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = check_cuda(fn, cudaFuncSetAttribute(jacobi_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (rc != LRS_OK) return rc;
-    rc = check_cuda(fn, cudaMemsetAsync(status_dev, 0, 3 * sizeof(int), st));
-    if (rc != LRS_OK) return rc;
     // rotate pairs whose cosine exceeds 1e-11; stop after a sweep whose largest rotated cosine was below 1e-6 (quadratic
-    // convergence: what is left is of order 1e-12); 30 sweeps is far beyond the 7-9 a Gram matrix takes (14 for a spectrum graded over 10 decades; exactly rank-deficient
-    // or degenerate matrices converge linearly in this parallel order: 17-22 sweeps)
+    // convergence: what is left is of order 1e-12); 30 sweeps is far beyond the 7-9 a Gram matrix takes (14 for a spectrum
+    // graded over 10 decades; exactly rank-deficient or degenerate matrices converge linearly in this parallel order: 17-22)
     const int we = w + (w & 1);
-    jacobi_eig_kernel<<<JC, 32 * we, smem, st>>>(G_dev, C, w, 1e-22, 1e-12, 30, lam_dev, Bt_dev, status_dev);
+    auto launch = [&](auto kern) -> int {
+        int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rc != LRS_OK) return rc;
+        rc = check_cuda(fn, cudaMemsetAsync(status_dev, 0, 3 * sizeof(int), st));
+        if (rc != LRS_OK) return rc;
+        kern<<<JC, 32 * we, smem, st>>>(G_dev, C, w, 1e-22, 1e-12, 30, lam_dev, Bt_dev, status_dev);
+        return LRS_OK;
+    };
+    const int rows = (C + 31) / 32;                    // rows of a column per lane
+    int rc = rows <= 2 ? launch(jacobi_eig_kernel<2>) : rows <= 4 ? launch(jacobi_eig_kernel<4>)
+           : rows <= 6 ? launch(jacobi_eig_kernel<6>) : launch(jacobi_eig_kernel<8>);
+    if (rc != LRS_OK) return rc;
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }

@@ -255,9 +255,9 @@ def ista(y, H, lambda_ista, alpha, Nit, *, denoiser: str = "soft", step: str = "
 # ------------------------------------------------------------------ SVT
 _EIGH_PAD_FROM, _EIGH_PAD_TO = 96, 136     # library path: band counts in [96, 136) are solved as a zero-bordered order-136 problem
 JACOBI_MAX_C = 256                         # lrs_sym_eig_jacobi_f64: one cluster, columns in distributed shared memory
-JACOBI_AUTO_C = 128                        # solver='auto' takes the Jacobi kernel up to this order (scripts/jacobi_time.py:
-#                                            0.20 / 0.37 / 0.91 ms against 0.35 / 0.99 / 1.14-1.2 ms of syevd at C = 31 / 64 / 128, and no host
-#                                            synchronisation; at C = 191 / 224 / 256 the library is as fast or faster: 1.74 / 2.4 / 3.2 vs 1.7 / 2.1 / 2.4 ms)
+JACOBI_AUTO_C = 192                        # solver='auto' takes the Jacobi kernel up to this order (scripts/jacobi_time.py:
+#                                            0.19 / 0.35 / 0.83 / 1.61 ms against 0.34 / 1.00 / 1.14-1.22 / 1.72 ms of syevd at C = 31 / 64 / 128 / 191,
+#                                            and no host synchronisation; at C = 224 / 256 the library is faster: 2.33 / 2.96 vs 2.06 / 2.42 ms)
 
 _DIVERGED = ("SVT: the band Gram matrix of X + lambda_2/mu_2 is not finite — the ADMM state has diverged "
              "(the reference's update lambda_1 += mu_1*(X - IMout) uses the overlap SUM, main_LRS_PnP.py:346,361; "
