@@ -38,6 +38,26 @@ K_ATOMS, NIT, BB, STRIDE = 256, 80, 8, 1
 METRIC, UNIT = "ista_patch_iters_per_s", "patch-iters/s"
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+# communicator, "NCCL version 2.28.9+cuda12.9"), so the process keeps a private handle to the original stdout for that
+# line and points file descriptor 1 at stderr for everything else.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -160,7 +180,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "pass_seconds_min_mean_max": [float(np.min(times)), mean, float(np.max(times))]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(w):
@@ -469,7 +489,7 @@ def run_ours(args, rank, world, local_rank):
                                                 "outside the timed region")
             if not parity < 1e-4:
                 raise SystemExit(f"bench.py: sharded run differs from the single-GPU run: rel-L2 {parity:.3e}")
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -517,13 +537,13 @@ def run_cfg1_reference(args, rank):
     mean = float(np.mean(times))
     val = P_s * CFG1_NIT / mean
     sample = f"{P_s} of the 144 patches (indices {list(CFG1_SAMPLE)}) x {CFG1_NIT} iterations per pass, literal per-patch loop with one SVD per patch"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    emit({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": 1e3 * mean, "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f32", "data": "bundled cube, synthetic dictionary",
                       "config": {"workload": CFG1_NAME, "patches_per_step": P_s, "patches_full_workload": 144, "extrapolated": False,
                                  "full_workload_ms_per_step_extrapolated": 1e3 * 144 * CFG1_NIT / val},
                       "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def run_cfg1_ours(args):
@@ -615,7 +635,7 @@ def run_cfg1_ours(args):
         P_s, dt = cfg1_cpu_pass(Y, D)
         cpu = {"value": P_s * CFG1_NIT / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{P_s} of the 144 patches x {CFG1_NIT} iterations, literal per-patch loop with one SVD per patch (B0)"}
-    print(json.dumps({
+    emit({
         "metric": METRIC, "value": P * CFG1_NIT / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": reps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 via 3-pass fp16 split on tcgen05 (22-bit operands, fp32 accumulate)", "data": "bundled cube, synthetic dictionary",
@@ -629,7 +649,7 @@ def run_cfg1_ours(args):
                      "traffic": None, "kernel": "sparse step = im2col + (2 Nit + 1) split-K tcgen05 GEMM/reduce launches", "kernel_ms": kms,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops {pk['bf16']:.0f} ({pk['src']}) / 3; informative only — "
                                     "144 patches cannot fill the tensor pipe, the path is launch/latency bound"},
-        "cpu_baseline": cpu}), flush=True)
+        "cpu_baseline": cpu})
 
 
 def main():
@@ -649,6 +669,7 @@ def main():
                     help="experiment: size (MiB) of each of the two Phi_z range buffers (default: SparseCoder.CHUNK_BYTES)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    claim_stdout()                                  # stdout carries the one JSON line and nothing else
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -138,7 +138,7 @@ __device__ __forceinline__ void jbar_wait(uint64_t* bar, uint32_t parity) {
 //   3. one thread arms its own mbarrier for the two incoming slots and sends its two slots to their next owners;
 //   4. wait for the incoming slots (own mbarrier), arm the cluster barrier, switch phase.
 // The stopping rule needs no verification sweep: Jacobi converges quadratically, so a sweep whose largest rotated cosine
-// was below 1e-6 leaves cosines of order 1e-12.
+// was below 3e-5 leaves cosines of order 1e-9.
 template <int JROWS>
 __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
     jacobi_eig_kernel(const double* __restrict__ G, int n, int w, double tol2, double stop2, int max_sweeps,
@@ -314,8 +314,8 @@ extern "C" int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_de
     if (w > JMAXW) return fail_arg(fn, "need 1 <= C <= 256");
     const size_t smem = (size_t)4 * ((size_t)w * C + 2) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
-    // rotate pairs whose cosine exceeds 1e-11; stop after a sweep whose largest rotated cosine was below 1e-6 (quadratic
-    // convergence: what is left is of order 1e-12); 30 sweeps is far beyond the 7-9 a Gram matrix takes (14 for a spectrum
+    // rotate pairs whose cosine exceeds 1e-11; stop after a sweep whose largest rotated cosine was below 3e-5 (quadratic
+    // convergence: what is left is of order 1e-9, two decades below what the fp32 weights W can resolve); 30 sweeps is far beyond the 7-9 a Gram matrix takes (14 for a spectrum
     // graded over 10 decades; exactly rank-deficient or degenerate matrices converge linearly in this parallel order: 17-22)
     const int we = w + (w & 1);
     auto launch = [&](auto kern) -> int {
@@ -323,7 +323,7 @@ extern "C" int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_de
         if (rc != LRS_OK) return rc;
         rc = check_cuda(fn, cudaMemsetAsync(status_dev, 0, 3 * sizeof(int), st));
         if (rc != LRS_OK) return rc;
-        kern<<<JC, 32 * we, smem, st>>>(G_dev, C, w, 1e-22, 1e-12, 30, lam_dev, Bt_dev, status_dev);
+        kern<<<JC, 32 * we, smem, st>>>(G_dev, C, w, 1e-22, 1e-9, 30, lam_dev, Bt_dev, status_dev);
         return LRS_OK;
     };
     const int rows = (C + 31) / 32;                    // rows of a column per lane
