@@ -27,6 +27,10 @@ int lrs_tc_timing_read(unsigned long long* out32_host);
  * (the caller zeroes it; a correct walk leaves every entry at 1), tiles_host receives the number of tiles.  bb = 8. */
 int lrs_debug_tile_walk(int64_t R, int64_t C, int bb, int s, int64_t p_begin, int64_t p_end, int sms, int* visits_host,
                         int64_t* tiles_host);
+/* HOST-side replay (no GPU needed) of ONE sweep of the parallel order of lrs_sym_eig_jacobi_f64 (csrc/jacobi_eig.cu) for C
+ * columns: meets_host[p*C + q] (p < q; caller zeroes C*C ints) counts how often columns p and q are paired — a correct order
+ * leaves every p < q at 1 —, conflicts_host the sub-rounds in which a column was used twice, subrounds_host their number. */
+int lrs_debug_jacobi_schedule(int C, int* meets_host, int* conflicts_host, int* subrounds_host);
 /* Cycle counts of MMA issue chains / TMEM load-store streams; out_dev = int64 [blocks*16]. */
 int lrs_tc_microbench(int do_mma, int f16, int ts, int N, int nacc, int ldst, int depth, int reps, int blocks,
                       long long* out_dev, lrs_stream_t stream);

@@ -59,6 +59,7 @@ DIAG_SIGNATURES = {
     "lrs_tc_probe_f32": (_int, [_p, _p, _p, _int, _int, _int, _int, _int, _p]),
     "lrs_tc_timing_read": (_int, [C.POINTER(C.c_uint64)]),
     "lrs_debug_tile_walk": (_int, [_i64, _i64, _int, _int, _i64, _i64, _int, _p, _p]),
+    "lrs_debug_jacobi_schedule": (_int, [_int, _p, _p, _p]),
     "lrs_tc_microbench": (_int, [_int, _int, _int, _int, _int, _int, _int, _int, _int, _p, _p]),
 }
 DIAG_LIB_PATH = os.path.join(_HERE, "csrc", "liblrs_pnp_diag.so")

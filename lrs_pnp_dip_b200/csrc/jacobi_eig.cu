@@ -22,6 +22,9 @@
 // meets exactly once per sweep: C - 1 + (C mod 2) sub-rounds, the minimum for a parallel Jacobi order.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -33,6 +36,50 @@ constexpr int JC = 8;              // CTAs per cluster (portable maximum)
 constexpr int JNB = 2 * JC;        // column blocks
 constexpr int JMAXW = 16;          // columns per block  -> C <= 256
 constexpr int JT = 32 * JMAXW;     // one warp per column pair of a sub-round
+
+// ---- the parallel Jacobi order, as pure index arithmetic (also compiled for the host: lrs_debug_jacobi_schedule replays a
+// sweep on the CPU and tests/test_host.py checks, without a GPU, that every pair of columns meets exactly once) ----
+// block width for C columns: ceil(C / 16), bumped so that a slot (w x C doubles) is a whole number of 16-byte words
+__host__ __device__ inline int jacobi_block_width(int C) {
+    int w = (C + JNB - 1) / JNB;
+    if ((w * C) & 1) ++w;
+    return w;
+}
+// cross pairs: in sub-round s warp i pairs top column i with this bottom column
+__host__ __device__ inline int jacobi_cross_partner(int i, int s, int w) {
+    const int jb = i + s;
+    return jb >= w ? jb - w : jb;
+}
+// pairs inside a block: circle method on `we` (even) players, sub-round s, pair i of we/2; columns >= w are byes
+__host__ __device__ inline void jacobi_circle_pair(int i, int s, int we, int& ca, int& cb) {
+    if (i == 0) {
+        ca = we - 1;
+        cb = s;
+    } else {
+        ca = (s + i) % (we - 1);
+        cb = (s - i + (we - 1)) % (we - 1);
+    }
+}
+// tournament move of the blocks after a round: top[0] stays, top[1] <- bot[0], top[i] <- top[i-1], bot[i] <- bot[i+1],
+// bot[JC-1] <- top[JC-1]; destination (CTA, slot 0 = top / 1 = bottom) of CTA `rank`'s two blocks
+__host__ __device__ inline void jacobi_move(int rank, int& top_to, int& top_slot, int& bot_to, int& bot_slot) {
+    if (rank == 0) {
+        top_to = 0;
+        top_slot = 0;
+        bot_to = 1 % JC;
+        bot_slot = 0;
+    } else {
+        if (rank < JC - 1) {
+            top_to = rank + 1;
+            top_slot = 0;
+        } else {
+            top_to = rank;
+            top_slot = 1;
+        }
+        bot_to = rank - 1;
+        bot_slot = 1;
+    }
+}
 
 // Orthogonalise columns p and q (n rows each, in shared memory) — one warp.  Returns the squared cosine of the angle it
 // removed (0 if the pair was left alone).
@@ -200,11 +247,7 @@ __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
             double* bot = slot(ph, 1);
             // every (top, bottom) pair: sub-round s pairs top column i with bottom column (i + s) mod w
             for (int s = 0; s < w; ++s) {
-                if (warp < w) {
-                    int jb = warp + s;
-                    jb = jb >= w ? jb - w : jb;
-                    rotate(top + (size_t)warp * n, bot + (size_t)jb * n);
-                }
+                if (warp < w) rotate(top + (size_t)warp * n, bot + (size_t)jacobi_cross_partner(warp, s, w) * n);
                 __syncthreads();
             }
             if (round == 0 && w > 1) {
@@ -215,13 +258,7 @@ __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
                     if (warp < we) {
                         const int sl = warp / half, i = warp - sl * half;
                         int ca, cb;
-                        if (i == 0) {
-                            ca = we - 1;
-                            cb = s;
-                        } else {
-                            ca = (s + i) % (we - 1);
-                            cb = (s - i + (we - 1)) % (we - 1);
-                        }
+                        jacobi_circle_pair(i, s, we, ca, cb);
                         if (ca < w && cb < w) {
                             double* base = sl ? bot : top;
                             rotate(base + (size_t)ca * n, base + (size_t)cb * n);
@@ -240,12 +277,7 @@ __global__ void __cluster_dims__(JC, 1, 1) __launch_bounds__(JT, 1)
             if (armed) cl.barrier_wait();                          // step 2: last round's blocks have landed everywhere
             if (tid == 0) {
                 int top_to, top_slot, bot_to, bot_slot;
-                if (rank == 0) { top_to = 0; top_slot = 0; bot_to = 1 % JC; bot_slot = 0; }
-                else {
-                    if (rank < JC - 1) { top_to = rank + 1; top_slot = 0; }
-                    else { top_to = rank; top_slot = 1; }
-                    bot_to = rank - 1; bot_slot = 1;
-                }
+                jacobi_move(rank, top_to, top_slot, bot_to, bot_slot);
                 if (round == JNB - 2) {                            // end of the sweep: my largest rotation to every CTA
                     for (int pr = 0; pr < JC; ++pr) cl.map_shared_rank(&max_cos2[0][0], pr)[(sweep & 1) * JC + rank] = my_max;
                     my_max = 0;
@@ -309,8 +341,7 @@ extern "C" int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_de
     const char* fn = "lrs_sym_eig_jacobi_f64";
     if (C < 1 || C > JNB * JMAXW) return fail_arg(fn, "need 1 <= C <= 256");
     if (!G_dev || !lam_dev || !Bt_dev || !status_dev) return fail_arg(fn, "null pointer");
-    int w = (C + JNB - 1) / JNB;
-    if ((w * C) & 1) ++w;                                          // even slot size: the exchange moves 16-byte words
+    const int w = jacobi_block_width(C);                           // even slot size: the exchange moves 16-byte words
     if (w > JMAXW) return fail_arg(fn, "need 1 <= C <= 256");
     const size_t smem = (size_t)4 * ((size_t)w * C + 2) * sizeof(double);
     cudaStream_t st = (cudaStream_t)stream;
@@ -333,3 +364,66 @@ extern "C" int lrs_sym_eig_jacobi_f64(const double* G_dev, int C, double* lam_de
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
+
+#ifdef LRS_DIAGNOSTICS
+#include "../../include/lrs_pnp_diag.h"
+
+// HOST replay of one sweep of the kernel's parallel order for C columns: meets_host[p * C + q] (p < q, caller zeroes) counts
+// how often columns p and q are paired; conflicts_host receives the number of sub-rounds in which a column appeared twice.
+extern "C" int lrs_debug_jacobi_schedule(int C, int* meets_host, int* conflicts_host, int* subrounds_host) {
+    const char* fn = "lrs_debug_jacobi_schedule";
+    if (C < 1 || C > JNB * JMAXW || !meets_host || !conflicts_host || !subrounds_host) return lrs::fail_arg(fn, "bad arguments");
+    const int w = jacobi_block_width(C), N = JNB * w;
+    if (w > JMAXW) return lrs::fail_arg(fn, "need 1 <= C <= 256");
+    int top[JC], bot[JC];
+    for (int i = 0; i < JC; ++i) {
+        top[i] = i;
+        bot[i] = i + JC;
+    }
+    int conflicts = 0, subrounds = 0;
+    std::vector<int> used(N);
+    auto meet = [&](int p, int q) {
+        if (used[p]++ || used[q]++) ++conflicts;
+        if (p < C && q < C) ++meets_host[(p < q ? p : q) * C + (p < q ? q : p)];
+    };
+    for (int round = 0; round < JNB - 1; ++round) {
+        for (int s = 0; s < w; ++s) {                                  // cross pairs, all CTAs in parallel
+            std::fill(used.begin(), used.end(), 0);
+            for (int c = 0; c < JC; ++c)
+                for (int i = 0; i < w; ++i) meet(top[c] * w + i, bot[c] * w + jacobi_cross_partner(i, s, w));
+            ++subrounds;
+        }
+        if (round == 0 && w > 1) {
+            const int we = w + (w & 1), half = we / 2;
+            for (int s = 0; s < we - 1; ++s) {
+                std::fill(used.begin(), used.end(), 0);
+                for (int c = 0; c < JC; ++c)
+                    for (int warp = 0; warp < we; ++warp) {
+                        const int sl = warp / half, i = warp - sl * half;
+                        int ca, cb;
+                        jacobi_circle_pair(i, s, we, ca, cb);
+                        if (ca < w && cb < w) meet((sl ? bot[c] : top[c]) * w + ca, (sl ? bot[c] : top[c]) * w + cb);
+                    }
+                ++subrounds;
+            }
+        }
+        int ntop[JC], nbot[JC], filled = 0;
+        for (int i = 0; i < JC; ++i) ntop[i] = nbot[i] = -1;
+        for (int r = 0; r < JC; ++r) {
+            int tt, ts, bt, bs;
+            jacobi_move(r, tt, ts, bt, bs);
+            (ts ? nbot : ntop)[tt] = top[r];
+            (bs ? nbot : ntop)[bt] = bot[r];
+        }
+        for (int i = 0; i < JC; ++i) filled += (ntop[i] >= 0) + (nbot[i] >= 0);
+        if (filled != 2 * JC) return lrs::fail_arg(fn, "the tournament move left a slot empty");
+        for (int i = 0; i < JC; ++i) {
+            top[i] = ntop[i];
+            bot[i] = nbot[i];
+        }
+    }
+    *conflicts_host = conflicts;
+    *subrounds_host = subrounds;
+    return LRS_OK;
+}
+#endif  // LRS_DIAGNOSTICS

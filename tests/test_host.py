@@ -154,3 +154,27 @@ def test_fused_kernel_tile_walk_covers_every_patch_once():
             assert rc == 0, (L.lrs_last_error(), R, Cc, s, b, e, sms)
             assert visits.min() == 1 and visits.max() == 1, (R, Cc, s, b, e, sms)
             assert (e - b + 127) // 128 <= tiles[0] <= (e - b + 127) // 128 + 2 * (Cc - 7) + 2
+
+
+def test_jacobi_eigensolver_schedule_pairs_every_two_columns_once():
+    """lrs_sym_eig_jacobi_f64 orders the column pairs of a sweep as a round-robin tournament of 16 column blocks over the 8
+    CTAs of a cluster (cross pairs every round, pairs inside a block in round 0).  lrs_debug_jacobi_schedule replays that
+    index arithmetic on the host: for every order 1..256 each pair of columns meets exactly once per sweep, no column is
+    used twice inside a sub-round, and the sweep has the minimum number of sub-rounds of a parallel order."""
+    from lrs_pnp_dip_b200 import _lib
+
+    L = _lib.diag_lib()
+    for C in range(1, 257):
+        meets = np.zeros((C, C), dtype=np.int32)
+        conflicts, subrounds = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        rc = L.lrs_debug_jacobi_schedule(C, meets.ctypes.data, conflicts.ctypes.data, subrounds.ctypes.data)
+        assert rc == 0, (C, L.lrs_last_error())
+        assert conflicts[0] == 0, C
+        iu = np.triu_indices(C, 1)
+        assert (meets[iu] == 1).all() and np.tril(meets).sum() == 0, C
+        w = -(-C // 16)
+        w += (w * C) & 1
+        assert subrounds[0] == 15 * w + ((w + (w & 1)) - 1 if w > 1 else 0), (C, subrounds[0])
+    meets = np.zeros(4, dtype=np.int32)
+    assert L.lrs_debug_jacobi_schedule(0, meets.ctypes.data, meets.ctypes.data, meets.ctypes.data) != 0
+    assert L.lrs_debug_jacobi_schedule(257, meets.ctypes.data, meets.ctypes.data, meets.ctypes.data) != 0
