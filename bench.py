@@ -319,6 +319,8 @@ def run_ours(args, rank, world, local_rank):
 
     sol = lrs.LRSPnP(torch.from_numpy(Yl), torch.from_numpy(Ml), torch.from_numpy(D), prm, engine=args.engine,
                      stripe=st if world > 1 else None, device=dev)
+    if args.no_hide:                                 # A/B: eigensolver after the sparse step instead of beside it
+        sol.hide_eigensolver = False
     coder = sol.be.coder
     # Time the dominant kernel with CUDA events on the launching stream.  The sparse step launches the fused kernel once
     # per range of column starts (two alternating streams, each range followed by its overlap-sum kernel, so that Phi_z is
@@ -465,7 +467,10 @@ def run_ours(args, rank, world, local_rank):
                                 "(main_LRS_PnP.py:228-229); the literal update diverges at stride 1 beyond ~20 iterations",
                        "l2": "inputs exceed L2 (every step streams %.1f GB of Phi_z through two %.2f GB range buffers)"
                              % (64 * P_local * 4 / 1e9, 64 * 4 * coder._chunk_cols() * (coder.R - BB + 1) / 1e9),
-                       "fused_launches_per_step": -(-(C - BB + 1) // coder._chunk_cols())},
+                       "fused_launches_per_step": -(-(C - BB + 1) // coder._chunk_cols()),
+                       "schedule": ("Gram first, Jacobi eigensolver on a high-priority stream beside the sparse step "
+                                    "(work items claimed dynamically), recomposition after it") if sol.hide_eigensolver
+                                   else "sparse step, then the low-rank step"},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                                    "d2h_bytes_per_step": d2h},
@@ -665,6 +670,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="cfg1: low-rank step after the sparse step instead of beside it")
+    ap.add_argument("--no-hide", action="store_true", help="eigensolver of the SVT after the sparse step instead of beside it")
     ap.add_argument("--range-mb", type=int, default=None,
                     help="experiment: size (MiB) of each of the two Phi_z range buffers (default: SparseCoder.CHUNK_BYTES)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -35,6 +35,9 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -122,6 +125,9 @@ struct __align__(8) Shared {
     uint64_t bar_G_full;      // loader -> epilogue: the gathered values of the next tile are in shared memory (loader warps)
     uint64_t bar_G_free;      // epilogue -> loader: the gather buffer has been consumed                      (NEPI warps)
     uint32_t tmem_base;
+    uint32_t ring_head;       // dynamic tile schedule: work items published so far (written by warp 1, lane 0)
+    uint32_t ring[8];         //   the last 8 of them
+    uint32_t ring_read[NTHREADS / 32];   // items every warp has read: a slot is reused only when all warps are past it
     float xmax[NCG][TILE];    // per-patch partial max |y| of the pixel groups
     float xsum[NCG][TILE];    // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
     uint32_t xrow[TILE];      // validity bits of window column 0 (pixels 0..7)
@@ -257,32 +263,69 @@ struct TilePlan {
     int64_t ci0, ci_end;   // column starts touched by [p_begin, p_end)
     int64_t items;         // rblocks * cchunks
     int cchunks, cpc;      // chunks per row block, column starts per chunk
+    unsigned* counter;     // device word, zero at launch: next unclaimed work item (nullptr: static round-robin deal)
 };
 
 // The walker also compiles for the host (lrs_debug_tile_walk below replays a launch's tile order on the CPU, so the
 // no-GPU test suite covers this integer logic); on the device the CTA index and the grid size stay special registers.
+//
+// Work items are CLAIMED, not dealt: a CTA takes the next unclaimed item from a device-wide counter, so a CTA that starts
+// late (its SM was busy with another kernel — the low-rank step's eigensolver runs beside the first launch of a sparse
+// step) or loses time simply claims fewer items, and no CTA ends a launch a whole item behind the others.  The three warp
+// roles of a CTA (gather, MMA, epilogue) each walk the same item sequence: warp 1 claims an item and publishes it in a
+// small shared-memory ring, the other warps read it from there and note how far they have read (a sub-range launch can
+// skip many items in a row, so the claiming warp checks those notes before it reuses a slot).  plan.counter == nullptr keeps the static deal (item = CTA, CTA +
+// grid, ...), which is also what the host replay walks.
 struct TileWalk {
     int64_t item;
     int rb = 0, ci = 0, c_hi = 0;
     int64_t stride_ = 0;                     // host replay only (never read on the device: optimised away)
-    __device__ TileWalk() : item((int64_t)blockIdx.x - (int64_t)gridDim.x) {}
+    Shared* sh_ = nullptr;                   // device, dynamic schedule
+    uint32_t nfetch_ = 0;
+    __device__ explicit TileWalk(Shared* sh) : item((int64_t)blockIdx.x - (int64_t)gridDim.x), sh_(sh) {}
     __host__ TileWalk(int64_t cta, int64_t grid) : item(cta - grid), stride_(grid) {}
-    __host__ __device__ __forceinline__ int64_t stride() const {
+    __host__ __device__ __forceinline__ int64_t next_item(const TilePlan& pl) {
 #ifdef __CUDA_ARCH__
-        return gridDim.x;
+        if (pl.counter == nullptr) return item + gridDim.x;
+        const uint32_t k = nfetch_++;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        uint32_t it = 0;
+        if (warp == 1) {                     // the claiming warp (whole warp, so that its lanes stay converged)
+            if (lane == 0) {
+                it = atomicAdd(pl.counter, 1u);
+                if (k >= 8) {                // slot k & 7 still holds item k - 8: every other warp must have read it
+                    for (int w = 0; w < NTHREADS / 32; ++w)
+                        while (w != 1 && *(volatile uint32_t*)&sh_->ring_read[w] < k - 7) {
+                        }
+                }
+                sh_->ring[k & 7] = it;
+                __threadfence_block();
+                *(volatile uint32_t*)&sh_->ring_head = k + 1;
+            }
+            it = __shfl_sync(0xffffffffu, it, 0);
+        } else {
+            while (*(volatile uint32_t*)&sh_->ring_head <= k) {
+            }
+            __threadfence_block();
+            it = *(volatile uint32_t*)&sh_->ring[k & 7];
+            __syncwarp();
+            if (lane == 0) *(volatile uint32_t*)&sh_->ring_read[warp] = k + 1;
+        }
+        return (int64_t)it;
 #else
-        return stride_;
+        (void)pl;
+        return item + stride_;
 #endif
     }
     // advance to this CTA's next tile holding at least one patch of [p_begin, p_end); pl and prm are the kernel
-    // parameters (constant bank), so the walker itself only keeps four values live across the iteration loop
+    // parameters (constant bank), so the walker itself only keeps a few values live across the iteration loop
     __host__ __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm) {
         const int64_t nR = prm.g.row.n;
         for (;;) {
             if (ci + 1 < c_hi) {
                 ++ci;
             } else {
-                item += stride();
+                item = next_item(pl);
                 if (item >= pl.items) return false;
                 rb = (int)(item / pl.cchunks);
                 ci = (int)(pl.ci0 + (item - (int64_t)rb * pl.cchunks) * pl.cpc);
@@ -347,7 +390,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     // The dictionary is normalised by an exact power of two, Dh = sd * D with max |Dh| in [0.5, 1), so that its
     // fp16 pieces are well scaled whatever the scale of D.  In "hat" units alpha_h = alpha'/sd, a_h = a sd^2:
     //     at_h <- soft(at_h + r Dh, lambda' sd / 2),   D alpha' = (Dh at_h) / a_h      (at_h = a_h alpha_h)
-    if (tid == 0) sh.dmax_bits = 0u;
+    if (tid == 0) {
+        sh.dmax_bits = 0u;
+        sh.ring_head = 0u;
+    }
+    if (tid < NTHREADS / 32) sh.ring_read[tid] = 0u;
     __syncthreads();
     {
         float mx = 0.f;
@@ -419,7 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0;
         long long dbg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_begin = TSTAMP();
-        for (TileWalk tw; tw.next(plan, prm);) {
+        for (TileWalk tw(&sh); tw.next(plan, prm);) {
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
@@ -522,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0, tcount = 0;
         long long ed[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long e_begin = TSTAMP();
-        for (TileWalk tw; tw.next(plan, prm);) {
+        for (TileWalk tw(&sh); tw.next(plan, prm);) {
             const long long tp0 = TSTAMP();
             // ---- tile prologue: gather my CW pixels, mask, step constant, scale.  Register slot c holds pixel
             //      16*(c/8) + 8*cg + c%8 = window row c%8, column 2*(c/8) + cg: every 16-pixel GEMM-B k-step is shared by
@@ -775,7 +822,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         const int lt = tid - 32;
         const int64_t C = prm.g.C;
         uint32_t t = 0;
-        for (TileWalk tw; tw.next(plan, prm); ++t) {
+        for (TileWalk tw(&sh); tw.next(plan, prm); ++t) {
             if (t > 0) mbar_wait(&sh.bar_G_free, (t - 1) & 1);
             for (int m = lt; m < TILE; m += NLOAD) {
                 const PatchRef pr = tile_patch(prm, tw, m);
@@ -833,7 +880,36 @@ static TilePlan make_tile_plan(const FusedParams& prm, int sms) {
     plan.cpc = (int)((ncols + cchunks - 1) / cchunks);
     plan.cchunks = (int)((ncols + plan.cpc - 1) / plan.cpc);   // no empty chunks: every work item holds tiles
     plan.items = rblocks * plan.cchunks;
+    plan.counter = nullptr;
     return plan;
+}
+
+// Claim counters of the dynamic tile schedule: a pool of words per device, one per launch in flight (a sparse step has two
+// launches in flight on its two streams; 64 slots cannot wrap around a launch that is still running).  LRS_STATIC_TILES=1
+// keeps the static deal for A/B measurements.
+static unsigned* claim_counter(cudaStream_t st) {
+    static const bool static_deal = getenv("LRS_STATIC_TILES") != nullptr;
+    if (static_deal) return nullptr;
+    constexpr int SLOTS = 64, MAXDEV = 64;
+    static unsigned* pool[MAXDEV] = {};
+    static std::atomic<unsigned> seq{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+    if (!pool[dev]) {
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        if (!pool[dev] && cudaMalloc(&pool[dev], SLOTS * sizeof(unsigned)) != cudaSuccess) {
+            pool[dev] = nullptr;
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+    }
+    unsigned* c = pool[dev] + (seq.fetch_add(1) % SLOTS);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned), st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return c;
 }
 
 template <int K>
@@ -852,8 +928,9 @@ static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     if (rc != LRS_OK) return rc;
     int sms = device_sm_count();
     if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
-    const TilePlan plan = make_tile_plan(prm, sms);
+    TilePlan plan = make_tile_plan(prm, sms);
     unsigned grid = (unsigned)(plan.items < sms ? plan.items : sms);
+    plan.counter = claim_counter(st);
     kern<<<grid, NTHREADS, smem, st>>>(prm, plan);
     note_launch();
     return check_cuda(fn, cudaGetLastError());

@@ -142,7 +142,8 @@ def _side_stream(device) -> "torch.cuda.Stream":
     """One extra stream per device for the low-rank step that runs beside the explicit sparse step (LRSPnP._step)."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=torch.device("cuda", key))
+        # high priority: its few CTAs (the 8-CTA eigensolver cluster) are placed before the sparse step's persistent grid
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=torch.device("cuda", key), priority=-1)
     return _SIDE_STREAMS[key]
 
 
@@ -422,8 +423,12 @@ class CudaBackend:
             self._pending.pop(0)
             ops.raise_for_eig_status(host)
 
-    def svt_apply(self, X, lambda_2, c, G, tau, rows):
-        W = ops.svt_weights(G, tau, status_sink=self._defer_status)
+    def svt_weights(self, G, tau):
+        return ops.svt_weights(G, tau, status_sink=self._defer_status)
+
+    def svt_apply(self, X, lambda_2, c, G, tau, rows, W=None):
+        if W is None:
+            W = self.svt_weights(G, tau)
         U = torch.empty((rows, X.shape[1]), dtype=torch.float32, device=X.device)
         check(lib().lrs_svt_apply_f32(ptr(X), ptr(lambda_2), float(c), ptr(W), rows, X.shape[1], ptr(U), stream_ptr()),
               "lrs_svt_apply_f32")
@@ -476,6 +481,11 @@ class LRSPnP:
                                  and self.stripe.world == 1)
         self._side = None
         self._late_inputs = None                         # from_host(): MtM / λ2 uploads still in flight on the side stream
+        # Fused engines: the persistent grid leaves no SM for a whole low-rank step, but the Jacobi eigensolver needs only
+        # 8 — it is launched (high-priority stream) right before the sparse step's first kernel and runs beside it; the
+        # fused kernel claims its work items dynamically, so the 8 CTAs that start late just take fewer of them.
+        self.hide_eigensolver = (isinstance(backend, CudaBackend) and coder is not None and coder.fused
+                                 and low_rank is None and Y_observed.shape[1] <= ops.JACOBI_AUTO_C)
 
     @classmethod
     def from_host(cls, Y_observed, MtM, D, prm: Params, state=None, device=None, **kw) -> "LRSPnP":
@@ -566,6 +576,22 @@ class LRSPnP:
                     U = low_rank_step()
             main.wait_stream(self._side)
             U.record_stream(main)                        # allocated on the side stream, consumed on the caller's
+        elif self.hide_eigensolver and self.low_rank is None and self._late_inputs is None:
+            # Gram (+ all-reduce) first, then the eigensolver on the side stream beside the whole sparse step; the
+            # recomposition follows the sparse step on the caller's stream.  (Right after from_host() λ2 is still being
+            # uploaded beside the sparse step: that one iteration keeps the sequential order below.)
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = _side_stream(self.X.device)
+            G = self.comm.allreduce_sum(be.gram(self.X, self.lambda_2, c, own))
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                W = be.svt_weights(G, 1.0 / prm.mu_2)
+            IMout = be.imout(self.X, self.lambda_1)      # its first launch is submitted behind the eigensolver's
+            self.comm.halo_reduce(IMout)
+            main.wait_stream(self._side)
+            W.record_stream(main)
+            U = be.svt_apply(self.X, self.lambda_2, c, G, 1.0 / prm.mu_2, own, W=W)
         else:
             # sparse step + overlap sum on the local rows (:259-303, :332-339)
             IMout = be.imout(self.X, self.lambda_1)
