@@ -305,12 +305,15 @@ def sparse_step(X, lambda_1, mu_1, Y_observed, D, bb, slidingDis, lambda_ista, N
     return (im, W, phi) if return_phi else (im, W)
 
 
-def admm_update(Y_observed, MtM, IMout, U, lambda_1, lambda_2, prm: Params, rows=None, row_offset=0, R_total=None):
-    """X / λ update (main_LRS_PnP.py:346,361-362).  λ1, λ2 are updated in place; returns X."""
+def admm_update(Y_observed, MtM, IMout, U, lambda_1, lambda_2, prm: Params, rows=None, row_offset=0, R_total=None, out=None):
+    """X / λ update (main_LRS_PnP.py:346,361-362).  λ1, λ2 are updated in place; returns X (written into ``out`` — a
+    contiguous [rows, C] fp32 tensor, e.g. the previous iterate, which the update does not read — when given)."""
     R, C = Y_observed.shape
     rows = R if rows is None else rows
     R_total = R if R_total is None else R_total
-    X = torch.empty((rows, C), dtype=torch.float32, device=Y_observed.device)
+    if out is not None and (out.shape != (rows, C) or out.dtype != torch.float32 or not out.is_contiguous()):
+        raise ValueError("out must be a contiguous float32 tensor of shape [rows, C]")
+    X = out if out is not None else torch.empty((rows, C), dtype=torch.float32, device=Y_observed.device)
     check(lib().lrs_admm_update_f32(ptr(Y_observed), ptr(MtM), ptr(IMout), ptr(U), ptr(lambda_1), ptr(lambda_2), ptr(X),
                                     float(prm.gamma), float(prm.mu_1), float(prm.mu_2), rows, row_offset, R_total, C,
                                     prm.bb, prm.slidingDis, stream_ptr()), "lrs_admm_update_f32")
@@ -439,8 +442,8 @@ class CudaBackend:
         check(lib().lrs_axpy_f32(ptr(X), ptr(L), float(c), ptr(out), out.numel(), stream_ptr()), "lrs_axpy_f32")
         return out
 
-    def admm_update(self, IMout, U, lambda_1, lambda_2, rows, row_offset, R_total):
-        return admm_update(self.Y, self.MtM, IMout, U, lambda_1, lambda_2, self.prm, rows, row_offset, R_total)
+    def admm_update(self, IMout, U, lambda_1, lambda_2, rows, row_offset, R_total, out=None):
+        return admm_update(self.Y, self.MtM, IMout, U, lambda_1, lambda_2, self.prm, rows, row_offset, R_total, out=out)
 
 
 class LRSPnP:
@@ -603,8 +606,10 @@ class LRSPnP:
             U = low_rank_step()
         # closed-form X, multipliers (:346, :361-362) on the owned rows
         self._late_inputs = None                         # every later use is ordered behind this step on the caller's stream
-        Xn = be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total)
-        self.X[:own] = Xn
+        if isinstance(be, CudaBackend):                 # the new iterate goes straight into X (the update never reads X)
+            be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total, out=self.X[:own])
+        else:
+            self.X[:own] = be.admm_update(IMout, U, self.lambda_1, self.lambda_2, own, row_off, st.R_total)
         self.comm.halo_refresh(self.X, self.lambda_1)
         self.iterations += 1
 
