@@ -164,13 +164,47 @@ def step_constants(blocks_copy: torch.Tensor, D: torch.Tensor, step: str) -> tor
     if step != "spectral":
         raise ValueError(f"unknown step mode {step!r}")
     m = (blocks_copy != 0).T.contiguous()                         # [P, n] bool
-    uniq, inv = torch.unique(m, dim=0, return_inverse=True)
+    # distinct patterns through two independent 64-bit hashes per patch (torch.unique(dim=0) sorts whole rows: ~10 ms for
+    # 144 x 1296); equal patterns hash equal, and the representatives are compared bit by bit below
+    gen = torch.Generator(device="cpu").manual_seed(0x5EED)
+    w = torch.randint(-(1 << 62), 1 << 62, (2, n), generator=gen, dtype=torch.int64).to(m.device)
+    h = torch.empty((P, 2), dtype=torch.int64, device=m.device)   # wrapping int64 arithmetic
+    chunk = max(1, (4 << 20) // max(n, 1))                        # bounded temporaries whatever P is
+    for p0 in range(0, P, chunk):
+        mm = m[p0:p0 + chunk].to(torch.int64)
+        h[p0:p0 + chunk, 0] = (mm * w[0]).sum(1)
+        h[p0:p0 + chunk, 1] = (mm * w[1]).sum(1)
+    _, inv = torch.unique(h, dim=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    n_u = int(inv.max()) + 1
+    rep = torch.full((n_u,), P, dtype=torch.int64, device=m.device).scatter_reduce(
+        0, inv, torch.arange(P, device=m.device), reduce="amin")
+    uniq = m[rep]
+    if not bool((uniq[inv] == m).all()):                          # a hash collision merged two patterns: exact fallback
+        uniq, inv = torch.unique(m, dim=0, return_inverse=True)
     if uniq.shape[0] > 4096:
         raise _lib.LrsError(f"{uniq.shape[0]} distinct mask patterns: spectral step constants need one eigensolve "
                             "each; use step='frob4' or pass explicit step constants")
-    vals = torch.tensor([spectral_norm_sq(D[uniq[u]]) for u in range(uniq.shape[0])], dtype=torch.float32,
-                        device=a.device)
+    # One eigensolve per distinct pattern AND dictionary, ever: the value depends on (D, pattern) only, the reference pays an
+    # SVD for it per patch per outer iteration, and an eigensolve of a 1296 x 1296 Gram matrix is ~10 ms — five outer
+    # iterations of configuration 1.  Memoised per dictionary TENSOR (address, in-place version, shape: as the row-pattern
+    # table below) and pattern bytes; the patterns travel to the host once (U x n bits).
+    dkey = (D.data_ptr(), D._version, tuple(D.shape), tuple(D.stride()), str(D.device))
+    packed = np.packbits(uniq.cpu().numpy(), axis=1)
+    vals = []
+    for u in range(uniq.shape[0]):
+        key = (dkey, packed[u].tobytes())
+        hit = _SPECTRAL_CACHE.get(key)
+        if hit is None:
+            if len(_SPECTRAL_CACHE) > 4096:
+                _SPECTRAL_CACHE.clear()
+            hit = _SPECTRAL_CACHE[key] = (D, spectral_norm_sq(D[uniq[u]]))
+        vals.append(hit[1])
+    vals = torch.tensor(vals, dtype=torch.float32, device=a.device)
     return vals[inv.reshape(-1)].contiguous()
+
+
+_SPECTRAL_CACHE: dict = {}
 
 
 def row_pattern_table(D: torch.Tensor, bb: int, step: str) -> torch.Tensor:
