@@ -330,10 +330,10 @@ def run_ours(args, rank, world, local_rank):
     kern_ev = []
     orig_imout = coder.imout
 
-    def timed_imout(X, l1):
+    def timed_imout(X, l1, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = orig_imout(X, l1)
+        out = orig_imout(X, l1, **kw)
         e1.record()
         kern_ev.append((e0, e1))
         return out

@@ -52,6 +52,10 @@ extern "C" {
 #define LRS_ENGINE_AUTO 0
 #define LRS_ENGINE_SIMT 1   /* fp32 FFMA kernel (any K multiple of 16 up to 256)          */
 #define LRS_ENGINE_TC 2     /* tcgen05/TMEM kernel, 3-pass fp16 split (n = 64, K in {64,128,192,256}) */
+/* OR-ed into `engine`: the tcgen05 kernel's CTAs CLAIM their work items from a device counter instead of being dealt them,
+ * for a launch that shares the GPU with another kernel (CTAs that start late take fewer items).  Costs ~4 % in cycles
+ * (DESIGN 3), so it is meant for that launch only. */
+#define LRS_ENGINE_DYNAMIC_TILES 0x100
 
 typedef void* lrs_stream_t;
 

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("LRS_PNP_LIB") or os.path.join(_HERE, "csrc", "liblrs_
 STEP_SPECTRAL, STEP_FROB4 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 ENGINES = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}
+ENGINE_DYNAMIC_TILES = 0x100          # OR-ed into the engine: work items claimed dynamically (include/lrs_pnp.h)
 DENOISERS = {"soft": 0, "nlm": 1, "identity": 2}
 
 _p = C.c_void_p

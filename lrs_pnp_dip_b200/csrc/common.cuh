@@ -129,7 +129,7 @@ int ista_tc_run(const float* blocks, const float* blocks_copy, const float* D, c
 // ista_generic.cu: A = NLmeansfilter(G, 3, 3, h_scale * T) column by column (NLmeansfilter.m:18-91)
 int nlm_columns(const char* fn, const float* G, const float* T, float h_scale, int K, int64_t P, float* A, cudaStream_t st);
 
-int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st);  // sparse_fused_tc.cu
+int sparse_fused_tc_launch(const FusedParams& prm, int K, bool dynamic_tiles, cudaStream_t st);  // sparse_fused_tc.cu
 bool sparse_fused_tc_supported(const FusedParams& prm, int K);
 
 }  // namespace lrs

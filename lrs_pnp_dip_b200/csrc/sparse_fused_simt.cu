@@ -208,10 +208,12 @@ extern "C" int lrs_sparse_step_fused_f32(const float* X_dev, const float* L_dev,
     prm.p_end = p_end;
     prm.phi = phi_z_dev;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool dynamic_tiles = (engine & LRS_ENGINE_DYNAMIC_TILES) != 0;     // tcgen05 engine only; ignored by the FFMA kernel
+    engine &= ~LRS_ENGINE_DYNAMIC_TILES;
     if (engine == LRS_ENGINE_TC || (engine == LRS_ENGINE_AUTO && sparse_fused_tc_supported(prm, K))) {
         if (!sparse_fused_tc_supported(prm, K))
             return fail_arg(fn, "tcgen05 engine needs K in {64,128,192,256}, Nit >= 1 and an sm_100 device");
-        return sparse_fused_tc_launch(prm, K, st);
+        return sparse_fused_tc_launch(prm, K, dynamic_tiles, st);
     }
     if (engine != LRS_ENGINE_SIMT && engine != LRS_ENGINE_AUTO) return fail_arg(fn, "unknown engine");
     switch (K) {

@@ -37,6 +37,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -128,6 +129,8 @@ struct __align__(8) Shared {
     uint32_t ring_head;       // dynamic tile schedule: work items published so far (written by warp 1, lane 0)
     uint32_t ring[8];         //   the last 8 of them
     uint32_t ring_read[NTHREADS / 32];   // items every warp has read: a slot is reused only when all warps are past it
+    uint32_t tiles_pub;       // tiles announced by the gather warps (the MMA warp does not walk: it only counts tiles)
+    uint32_t walk_done;       // set after the last announcement
     float xmax[NCG][TILE];    // per-patch partial max |y| of the pixel groups
     float xsum[NCG][TILE];    // per-patch partial sum of valid row norms (in-kernel 4||H||_F^2)
     uint32_t xrow[TILE];      // validity bits of window column 0 (pixels 0..7)
@@ -273,29 +276,31 @@ struct TilePlan {
 // late (its SM was busy with another kernel — the low-rank step's eigensolver runs beside the first launch of a sparse
 // step) or loses time simply claims fewer items, and no CTA ends a launch a whole item behind the others.  The three warp
 // roles of a CTA (gather, MMA, epilogue) each walk the same item sequence: warp 1 claims an item and publishes it in a
-// small shared-memory ring, the other warps read it from there and note how far they have read (a sub-range launch can
+// small shared-memory ring, the other walking warps (gather, epilogue) read it from there and note how far they have read (a sub-range launch can
 // skip many items in a row, so the claiming warp checks those notes before it reuses a slot).  plan.counter == nullptr keeps the static deal (item = CTA, CTA +
 // grid, ...), which is also what the host replay walks.
 struct TileWalk {
     int64_t item;
     int rb = 0, ci = 0, c_hi = 0;
     int64_t stride_ = 0;                     // host replay only (never read on the device: optimised away)
-    Shared* sh_ = nullptr;                   // device, dynamic schedule
-    uint32_t nfetch_ = 0;
-    __device__ explicit TileWalk(Shared* sh) : item((int64_t)blockIdx.x - (int64_t)gridDim.x), sh_(sh) {}
+    // The walker keeps NO extra state for the dynamic schedule (the epilogue warps have no register to spare): how many
+    // items a warp has read is kept in shared memory (ring_read[warp]; ring_head for the claiming warp itself).
+    __device__ TileWalk() : item((int64_t)blockIdx.x - (int64_t)gridDim.x) {}
     __host__ TileWalk(int64_t cta, int64_t grid) : item(cta - grid), stride_(grid) {}
-    __host__ __device__ __forceinline__ int64_t next_item(const TilePlan& pl) {
+    template <bool DYN>
+    __host__ __device__ __forceinline__ int64_t next_item(const TilePlan& pl, Shared* sh_) {
 #ifdef __CUDA_ARCH__
-        if (pl.counter == nullptr) return item + gridDim.x;
-        const uint32_t k = nfetch_++;
+        if (!DYN) return item + gridDim.x;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const uint32_t k = *(volatile uint32_t*)(warp == 1 ? &sh_->ring_head : &sh_->ring_read[warp]);
         uint32_t it = 0;
         if (warp == 1) {                     // the claiming warp (whole warp, so that its lanes stay converged)
+            __syncwarp();                    // every lane has read k before lane 0 moves ring_head
             if (lane == 0) {
                 it = atomicAdd(pl.counter, 1u);
                 if (k >= 8) {                // slot k & 7 still holds item k - 8: every other warp must have read it
-                    for (int w = 0; w < NTHREADS / 32; ++w)
-                        while (w != 1 && *(volatile uint32_t*)&sh_->ring_read[w] < k - 7) {
+                    for (int w = 2; w < NTHREADS / 32; ++w)      // warps 2.. walk (warp 0, the MMA warp, only counts tiles)
+                        while (*(volatile uint32_t*)&sh_->ring_read[w] < k - 7) {
                         }
                 }
                 sh_->ring[k & 7] = it;
@@ -310,22 +315,25 @@ struct TileWalk {
             it = *(volatile uint32_t*)&sh_->ring[k & 7];
             __syncwarp();
             if (lane == 0) *(volatile uint32_t*)&sh_->ring_read[warp] = k + 1;
+            __syncwarp();                    // the next call's lanes read the updated count
         }
         return (int64_t)it;
 #else
         (void)pl;
+        (void)sh_;
         return item + stride_;
 #endif
     }
     // advance to this CTA's next tile holding at least one patch of [p_begin, p_end); pl and prm are the kernel
     // parameters (constant bank), so the walker itself only keeps a few values live across the iteration loop
-    __host__ __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm) {
+    template <bool DYN = false>
+    __host__ __device__ __forceinline__ bool next(const TilePlan& pl, const FusedParams& prm, Shared* sh = nullptr) {
         const int64_t nR = prm.g.row.n;
         for (;;) {
             if (ci + 1 < c_hi) {
                 ++ci;
             } else {
-                item = next_item(pl);
+                item = next_item<DYN>(pl, sh);
                 if (item >= pl.items) return false;
                 rb = (int)(item / pl.cchunks);
                 ci = (int)(pl.ci0 + (item - (int64_t)rb * pl.cchunks) * pl.cpc);
@@ -369,7 +377,11 @@ __host__ __device__ __forceinline__ PatchRef tile_patch(const FusedParams& prm, 
 // KATOMS in {64, 128, 192, 256}: the state occupies TMEM columns [0, KATOMS); GEMM-B is issued in two halves of KATOMS/2 atoms.
 // FOLD: the masks are band-replicated (the a_table step-constant mode, whose table is indexed by the validity of the 8 window
 // rows): the mask is folded into the residual constants, see the residual phase.
-template <bool DBG, int KATOMS, bool FOLD>
+// DYN: work items claimed dynamically (see TileWalk); the static instance keeps every loop of the MMA warp warp-uniform in the
+// compiler's eyes — with the claimed item arriving through shared memory ptxas spills uniform registers around the MMA groups
+// (+3.8 % cycles per launch, ncu tensor pipe 74.0 instead of 76.9 %) — so the dynamic instance is used only for the launch
+// that has to share the GPU (the first of a sparse step, beside the eigensolver).
+template <bool DBG, int KATOMS, bool FOLD, bool DYN>
 __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParams prm, TilePlan plan) {
     constexpr int NCHUNK = KATOMS / 64;
     constexpr int KH = KATOMS / 2;                    // atoms per GEMM-B half (MMA N)
@@ -393,6 +405,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
     if (tid == 0) {
         sh.dmax_bits = 0u;
         sh.ring_head = 0u;
+        sh.tiles_pub = 0u;
+        sh.walk_done = 0u;
     }
     if (tid < NTHREADS / 32) sh.ring_read[tid] = 0u;
     __syncthreads();
@@ -466,7 +480,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0;
         long long dbg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_begin = TSTAMP();
-        for (TileWalk tw(&sh); tw.next(plan, prm);) {
+        // Dynamic instance: the MMA warp does not walk the tiles (it needs no coordinates); the gather warps announce every tile
+        // they find and the vote makes the loop condition warp-uniform.  Static instance: the walker itself (all uniform).
+        TileWalk twm;
+        uint32_t nt = 0;
+        auto more_tiles = [&]() -> bool {
+            if constexpr (DYN) {
+                uint32_t have;
+                for (;;) {
+                    have = *(volatile uint32_t*)&sh.tiles_pub;
+                    if (have > nt) break;
+                    if (*(volatile uint32_t*)&sh.walk_done) {
+                        __threadfence_block();
+                        have = *(volatile uint32_t*)&sh.tiles_pub;   // the last announcement precedes walk_done
+                        break;
+                    }
+                }
+                const bool ok = __all_sync(0xffffffffu, have > nt);
+                ++nt;
+                return ok;
+            } else {
+                return twm.next<false>(plan, prm);
+            }
+        };
+        while (more_tiles()) {
             for (int it = 0; it < Nit; ++it, ++gi) {
                 const uint32_t par = gi & 1;
                 // ---- GEMM-B: state += r D; k-step ks (16 pixels) starts as soon as its residual quarter is staged ----
@@ -569,7 +606,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         uint32_t gi = 0, tcount = 0;
         long long ed[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const long long e_begin = TSTAMP();
-        for (TileWalk tw(&sh); tw.next(plan, prm);) {
+        for (TileWalk tw; tw.next<DYN>(plan, prm, &sh);) {
             const long long tp0 = TSTAMP();
             // ---- tile prologue: gather my CW pixels, mask, step constant, scale.  Register slot c holds pixel
             //      16*(c/8) + 8*cg + c%8 = window row c%8, column 2*(c/8) + cg: every 16-pixel GEMM-B k-step is shared by
@@ -822,7 +859,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
         const int lt = tid - 32;
         const int64_t C = prm.g.C;
         uint32_t t = 0;
-        for (TileWalk tw(&sh); tw.next(plan, prm); ++t) {
+        for (TileWalk tw; tw.next<DYN>(plan, prm, &sh); ++t) {
+            if (DYN && tid == 32) *(volatile uint32_t*)&sh.tiles_pub = t + 1;      // announce the tile to the MMA warp
             if (t > 0) mbar_wait(&sh.bar_G_free, (t - 1) & 1);
             for (int m = lt; m < TILE; m += NLOAD) {
                 const PatchRef pr = tile_patch(prm, tw, m);
@@ -850,6 +888,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sparse_fused_tc_kernel(FusedParam
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.bar_G_full);
+        }
+        if (DYN && tid == 32) {                            // no more tiles (after the last announcement)
+            __threadfence_block();
+            *(volatile uint32_t*)&sh.walk_done = 1u;
         }
     }
     tc_fence_before();
@@ -885,11 +927,8 @@ static TilePlan make_tile_plan(const FusedParams& prm, int sms) {
 }
 
 // Claim counters of the dynamic tile schedule: a pool of words per device, one per launch in flight (a sparse step has two
-// launches in flight on its two streams; 64 slots cannot wrap around a launch that is still running).  LRS_STATIC_TILES=1
-// keeps the static deal for A/B measurements.
+// launches in flight on its two streams; 64 slots cannot wrap around a launch that is still running).
 static unsigned* claim_counter(cudaStream_t st) {
-    static const bool static_deal = getenv("LRS_STATIC_TILES") != nullptr;
-    if (static_deal) return nullptr;
     constexpr int SLOTS = 64, MAXDEV = 64;
     static unsigned* pool[MAXDEV] = {};
     static std::atomic<unsigned> seq{0};
@@ -913,16 +952,21 @@ static unsigned* claim_counter(cudaStream_t st) {
 }
 
 template <int K>
-static int launch_tc(const FusedParams& prm, cudaStream_t st) {
+static int launch_tc(const FusedParams& prm, bool dynamic_tiles, cudaStream_t st) {
     const char* fn = "lrs_sparse_step_fused_f32";
     const size_t smem = D_SMEM_BYTES + R_SMEM_BYTES + G_SMEM_BYTES + sizeof(Shared);
     const bool fold = LRS_MASK_FOLD && prm.a_table != nullptr && prm.a_patch == nullptr;
+    using Kern = void (*)(FusedParams, TilePlan);
+    auto pick = [&](auto dbg_c, bool dyn) -> Kern {
+        constexpr bool DBGV = decltype(dbg_c)::value;
+        if (dyn) return fold ? sparse_fused_tc_kernel<DBGV, K, true, true> : sparse_fused_tc_kernel<DBGV, K, false, true>;
+        return fold ? sparse_fused_tc_kernel<DBGV, K, true, false> : sparse_fused_tc_kernel<DBGV, K, false, false>;
+    };
 #ifdef LRS_DIAGNOSTICS   // liblrs_pnp_diag.so only: barrier-wait counters (include/lrs_pnp_diag.h)
     static const bool dbg = getenv("LRS_TC_TIMING") != nullptr;
-    auto kern = dbg ? (fold ? sparse_fused_tc_kernel<true, K, true> : sparse_fused_tc_kernel<true, K, false>)
-                    : (fold ? sparse_fused_tc_kernel<false, K, true> : sparse_fused_tc_kernel<false, K, false>);
+    Kern kern = dbg ? pick(std::true_type{}, dynamic_tiles) : pick(std::false_type{}, dynamic_tiles);
 #else
-    auto kern = fold ? sparse_fused_tc_kernel<false, K, true> : sparse_fused_tc_kernel<false, K, false>;
+    Kern kern = pick(std::false_type{}, dynamic_tiles);
 #endif
     int rc = check_cuda(fn, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc != LRS_OK) return rc;
@@ -930,20 +974,21 @@ static int launch_tc(const FusedParams& prm, cudaStream_t st) {
     if (sms <= 0) return check_cuda(fn, cudaErrorNoDevice);
     TilePlan plan = make_tile_plan(prm, sms);
     unsigned grid = (unsigned)(plan.items < sms ? plan.items : sms);
-    plan.counter = claim_counter(st);
+    plan.counter = dynamic_tiles ? claim_counter(st) : nullptr;
+    if (dynamic_tiles && !plan.counter) return fail_arg(fn, "no claim counter for the dynamic tile schedule");
     kern<<<grid, NTHREADS, smem, st>>>(prm, plan);
     note_launch();
     return check_cuda(fn, cudaGetLastError());
 }
 
-int sparse_fused_tc_launch(const FusedParams& prm, int K, cudaStream_t st) {
+int sparse_fused_tc_launch(const FusedParams& prm, int K, bool dynamic_tiles, cudaStream_t st) {
     if (!sparse_fused_tc_supported(prm, K))
         return fail_arg("lrs_sparse_step_fused_f32", "tcgen05 engine needs K in {64,128,192,256}, Nit >= 1 and an sm_100 device");
     switch (K) {
-        case 64: return launch_tc<64>(prm, st);
-        case 128: return launch_tc<128>(prm, st);
-        case 192: return launch_tc<192>(prm, st);
-        default: return launch_tc<256>(prm, st);
+        case 64: return launch_tc<64>(prm, dynamic_tiles, st);
+        case 128: return launch_tc<128>(prm, dynamic_tiles, st);
+        case 192: return launch_tc<192>(prm, dynamic_tiles, st);
+        default: return launch_tc<256>(prm, dynamic_tiles, st);
     }
 }
 

@@ -227,14 +227,16 @@ class SparseCoder:
                                   denoiser=prm.denoiser, h_scale=prm.nlm_h_scale)
         return phi
 
-    def _fused_range(self, X, lambda_1, p_begin: int, p_end: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _fused_range(self, X, lambda_1, p_begin: int, p_end: int, out: Optional[torch.Tensor] = None,
+                     dynamic: bool = False) -> torch.Tensor:
         prm = self.prm
         if out is None:
             out = torch.empty((self.n, p_end - p_begin), dtype=torch.float32, device=X.device)
         check(lib().lrs_sparse_step_fused_f32(ptr(X), ptr(lambda_1), float(prm.mu_1), ptr(self.Y), ptr(self.D), self.K,
                                               ptr(self.a_patch), ptr(self.a_table), float(prm.lambda_ista), int(prm.Nit),
                                               self.R, self.C, prm.bb, prm.slidingDis, p_begin, p_end, ptr(out),
-                                              self.engine, stream_ptr()), "lrs_sparse_step_fused_f32")
+                                              self.engine | (_lib.ENGINE_DYNAMIC_TILES if dynamic else 0), stream_ptr()),
+              "lrs_sparse_step_fused_f32")
         return out
 
     def phi_z_range(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor], p_begin: int, p_end: int) -> torch.Tensor:
@@ -258,13 +260,17 @@ class SparseCoder:
         nR = self.R - self.prm.bb + 1
         return max(1, int(self.CHUNK_BYTES // (nR * self.n * 4)))
 
-    def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor]) -> torch.Tensor:
-        """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339)."""
+    def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor], shared_start: bool = False) -> torch.Tensor:
+        """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339).  ``shared_start``: another kernel holds a
+        few SMs while the first launch starts (the eigensolver of the low-rank step): that launch claims its work items
+        dynamically, so the CTAs that start late take fewer of them."""
         prm = self.prm
         with _on(X):
             nC = self.C - prm.bb + 1
             if not (self.fused and prm.slidingDis == 1) or self._chunk_cols() >= nC:
-                return ops.col2im(self.phi_z(X, lambda_1), self.R, self.C, prm.bb, prm.slidingDis)
+                self.validate(wait=False)
+                phi = self._fused_range(X, lambda_1, 0, self.P, dynamic=shared_start) if self.fused else self._phi_z(X, lambda_1)
+                return ops.col2im(phi, self.R, self.C, prm.bb, prm.slidingDis)
             self.validate(wait=False)
             nR, cpc = self.R - prm.bb + 1, self._chunk_cols()
             pipe = _range_pipe(X.device)
@@ -281,7 +287,8 @@ class SparseCoder:
                     st.wait_event(ready)                      # inputs (and `out`) are ready on the caller's stream
                 with torch.cuda.stream(st):
                     buf = bufs[k & 1][:self.n * (c1 - c0) * nR].view(self.n, (c1 - c0) * nR)
-                    self._fused_range(X, lambda_1, c0 * nR, c1 * nR, out=buf)   # buffer k&1 was released by sum k-2 (same stream)
+                    self._fused_range(X, lambda_1, c0 * nR, c1 * nR, out=buf,   # buffer k&1 was released by sum k-2 (same stream)
+                                      dynamic=shared_start and k == 0)
                     if prev_sum is not None:
                         st.wait_event(prev_sum)               # running sum: range k continues where range k-1 stopped
                     check(lib().lrs_col2im_accum_range_f32(ptr(buf), self.R, self.C, prm.bb, prm.slidingDis, c0, c1, ptr(out),
@@ -398,8 +405,8 @@ class CudaBackend:
         self.coder = SparseCoder(Y_local, D, prm, engine, defer_validation=True)
         self._pending: list = []
 
-    def imout(self, X, lambda_1):
-        return self.coder.imout(X, lambda_1)
+    def imout(self, X, lambda_1, shared_start=False):
+        return self.coder.imout(X, lambda_1, shared_start=shared_start)
 
     def gram(self, X, lambda_2, c, rows):
         C = X.shape[1]
@@ -592,7 +599,7 @@ class LRSPnP:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 W = be.svt_weights(G, 1.0 / prm.mu_2, solver="jacobi")
-            IMout = be.imout(self.X, self.lambda_1)      # its first launch is submitted behind the eigensolver's
+            IMout = be.imout(self.X, self.lambda_1, shared_start=True)   # first launch behind the eigensolver's: dynamic deal
             self.comm.halo_reduce(IMout)
             main.wait_stream(self._side)
             W.record_stream(main)
