@@ -467,7 +467,7 @@ def run_ours(args, rank, world, local_rank):
                                 "(main_LRS_PnP.py:228-229); the literal update diverges at stride 1 beyond ~20 iterations",
                        "l2": "inputs exceed L2 (every step streams %.1f GB of Phi_z through two %.2f GB range buffers)"
                              % (64 * P_local * 4 / 1e9, 64 * 4 * coder._chunk_cols() * (coder.R - BB + 1) / 1e9),
-                       "fused_launches_per_step": -(-(C - BB + 1) // coder._chunk_cols()),
+                       "fused_launches_per_step": len(coder._ranges(sol.hide_eigensolver)),
                        "schedule": ("Gram first, Jacobi eigensolver on a high-priority stream beside the sparse step "
                                     "(work items claimed dynamically), recomposition after it") if sol.hide_eigensolver
                                    else "sparse step, then the low-rank step"},

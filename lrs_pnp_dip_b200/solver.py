@@ -260,6 +260,26 @@ class SparseCoder:
         nR = self.R - self.prm.bb + 1
         return max(1, int(self.CHUNK_BYTES // (nR * self.n * 4)))
 
+    # A launch that shares the GPU with the eigensolver (shared_start) uses the dynamically dealt kernel instance, which
+    # needs ~4 % more cycles: that first range is kept just long enough to cover the eigensolver (~2 ms), judged by the
+    # kernel's rate on a B200.
+    SHARED_START_SECONDS = 2.5e-3
+    FUSED_PATCH_ITERS_PER_S = 6.5e9
+
+    def _ranges(self, shared_start: bool = False):
+        """Column-start ranges [(c0, c1), ...] of one sparse step, ascending and contiguous."""
+        prm = self.prm
+        nR, nC, cpc = self.R - prm.bb + 1, self.C - prm.bb + 1, self._chunk_cols()
+        out, c0 = [], 0
+        if shared_start:
+            first = int(np.ceil(self.SHARED_START_SECONDS * self.FUSED_PATCH_ITERS_PER_S / (nR * max(prm.Nit, 1))))
+            c0 = min(nC, max(1, min(cpc, first)))
+            out.append((0, c0))
+        while c0 < nC:
+            out.append((c0, min(nC, c0 + cpc)))
+            c0 += cpc
+        return out
+
     def imout(self, X: torch.Tensor, lambda_1: Optional[torch.Tensor], shared_start: bool = False) -> torch.Tensor:
         """Overlap sum of the reconstructed patches (main_LRS_PnP.py:332-339).  ``shared_start``: another kernel holds a
         few SMs while the first launch starts (the eigensolver of the low-rank step): that launch claims its work items
@@ -280,8 +300,7 @@ class SparseCoder:
             ready = torch.cuda.Event()
             ready.record(main)
             prev_sum = None
-            for k, c0 in enumerate(range(0, nC, cpc)):
-                c1 = min(nC, c0 + cpc)
+            for k, (c0, c1) in enumerate(self._ranges(shared_start)):
                 st = streams[k & 1]
                 if k < 2:
                     st.wait_event(ready)                      # inputs (and `out`) are ready on the caller's stream
