@@ -178,3 +178,29 @@ def test_jacobi_eigensolver_schedule_pairs_every_two_columns_once():
     meets = np.zeros(4, dtype=np.int32)
     assert L.lrs_debug_jacobi_schedule(0, meets.ctypes.data, meets.ctypes.data, meets.ctypes.data) != 0
     assert L.lrs_debug_jacobi_schedule(257, meets.ctypes.data, meets.ctypes.data, meets.ctypes.data) != 0
+
+
+def test_sparse_step_column_ranges_are_contiguous_and_start_short_when_shared():
+    """SparseCoder._ranges (pure host logic): ascending, contiguous column-start ranges that cover every column start once;
+    with shared_start the first range is the short one that runs on the dynamically dealt kernel instance (about 2.5 ms of
+    work, never longer than a regular range), the rest are regular."""
+    from lrs_pnp_dip_b200.solver import Params, SparseCoder
+
+    class Fake(SparseCoder):
+        def __init__(self, R, C, Nit):
+            self.R, self.C, self.n, self.prm = R, C, 64, Params(Nit=Nit, bb=8, slidingDis=1)
+
+    for R, C, Nit in ((262144, 191, 80), (32775, 191, 80), (1048576, 224, 80), (700, 29, 10), (131079, 191, 100), (4096, 9, 1)):
+        f = Fake(R, C, Nit)
+        nC, cpc = C - 7, f._chunk_cols()
+        for shared in (False, True):
+            r = f._ranges(shared)
+            assert r[0][0] == 0 and r[-1][1] == nC and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(0 < c1 - c0 <= cpc for c0, c1 in r)
+            if not shared:
+                assert len(r) == -(-nC // cpc)
+        first = f._ranges(True)[0]
+        work_s = (first[1] - first[0]) * (R - 7) * Nit / SparseCoder.FUSED_PATCH_ITERS_PER_S
+        assert first[1] - first[0] == min(cpc, nC) or work_s >= SparseCoder.SHARED_START_SECONDS * 0.999
+        assert first[1] - first[0] == 1 or (first[1] - first[0] - 1) * (R - 7) * Nit / SparseCoder.FUSED_PATCH_ITERS_PER_S \
+            < SparseCoder.SHARED_START_SECONDS

@@ -238,3 +238,37 @@ def test_literal_loop_port_matches_reference_and_oracle():
                 y, H = ns["delete_element"](y, miss.tolist()), ns["delete_element"](H, miss.tolist())
             lit = torch.mm(torch.tensor(D), ns["ista"](y, H, 0.1, 0, 30)).flatten().numpy()
             assert rel(phi[:, jj], lit) < 1e-5, jj
+
+
+def test_svt_through_the_b_form_of_a_one_sided_jacobi_sweep():
+    """The math behind lrs_sym_eig_jacobi_f64 + lrs_svt_weights_f64, on the CPU: orthogonalising the columns of
+    the band Gram matrix G = Z^T Z by plane rotations gives B = G V with column k = lambda_k v_k, and
+    W = sum_k b_k b_k^T max(1 - tau/sqrt(lambda_k), 0) / lambda_k^2 reproduces SVT(Z, tau) = Z W (main_LRS_PnP.py:118-124)."""
+    rng = np.random.default_rng(3)
+    Z = (rng.standard_normal((400, 4)) @ rng.standard_normal((4, 24)) + 0.05 * rng.standard_normal((400, 24))).astype(np.float32)
+    G = Z.astype(np.float64).T @ Z.astype(np.float64)
+    B = G.copy()
+    for _ in range(12):                                   # cyclic one-sided Jacobi (any order that meets every pair works)
+        worst = 0.0
+        for p in range(24):
+            for q in range(p + 1, 24):
+                a, b, g = B[:, p] @ B[:, p], B[:, q] @ B[:, q], B[:, p] @ B[:, q]
+                if g * g <= 1e-22 * a * b:
+                    continue
+                worst = max(worst, g * g / (a * b))
+                d, h = b - a, 2.0 * g
+                t = (h if d >= 0 else -h) / (abs(d) + np.sqrt(d * d + h * h))
+                c = 1.0 / np.sqrt(1.0 + t * t)
+                s = c * t
+                B[:, p], B[:, q] = c * B[:, p] - s * B[:, q], s * B[:, p] + c * B[:, q]
+        if worst <= 1e-9:
+            break
+    lam = np.linalg.norm(B, axis=0)
+    assert np.abs(np.sort(lam) - np.linalg.eigvalsh(G)).max() <= 1e-9 * lam.max()
+    for tau in (1.0 / 0.9, 3.0):
+        sigma = np.sqrt(lam)
+        w = np.where((sigma > tau) & (lam > 1e-12 * lam.max()), (1.0 - tau / np.maximum(sigma, 1e-300)) / lam ** 2, 0.0)
+        W = (B * w[None, :]) @ B.T
+        got = Z.astype(np.float64) @ W
+        want = orc.svt(Z, tau)
+        assert np.linalg.norm(got - want) <= 1e-5 * np.linalg.norm(want)
