@@ -272,13 +272,13 @@ struct TilePlan {
 // The walker also compiles for the host (lrs_debug_tile_walk below replays a launch's tile order on the CPU, so the
 // no-GPU test suite covers this integer logic); on the device the CTA index and the grid size stay special registers.
 //
-// Work items are CLAIMED, not dealt: a CTA takes the next unclaimed item from a device-wide counter, so a CTA that starts
-// late (its SM was busy with another kernel — the low-rank step's eigensolver runs beside the first launch of a sparse
-// step) or loses time simply claims fewer items, and no CTA ends a launch a whole item behind the others.  The three warp
-// roles of a CTA (gather, MMA, epilogue) each walk the same item sequence: warp 1 claims an item and publishes it in a
-// small shared-memory ring, the other walking warps (gather, epilogue) read it from there and note how far they have read (a sub-range launch can
-// skip many items in a row, so the claiming warp checks those notes before it reuses a slot).  plan.counter == nullptr keeps the static deal (item = CTA, CTA +
-// grid, ...), which is also what the host replay walks.
+// Two deals (template parameter DYN of next()).  Static: item = CTA, CTA + grid, ... — also what the host replay walks.
+// Dynamic: work items are CLAIMED — a CTA takes the next unclaimed item from a device-wide counter, so a CTA that starts late
+// (its SM was busy with another kernel: the low-rank step's eigensolver runs beside the first launch of a sparse step) simply
+// claims fewer items.  Warp 1 claims an item and publishes it in a small shared-memory ring; the other walking warps (gather,
+// epilogue) read it from there and note how far they have read (a sub-range launch can skip many items in a row, so the
+// claiming warp checks those notes before it reuses a slot).  The MMA warp does not walk in the dynamic instance: it counts
+// the tiles the gather warps announce (see the kernel).
 struct TileWalk {
     int64_t item;
     int rb = 0, ci = 0, c_hi = 0;
